@@ -1,0 +1,189 @@
+/*
+ * nmsv.h -- C ABI of libnmsv_sw.so: B200 (sm_100a) engine for nanomonsv's supporting-read validation path.
+ *
+ * Plain C linkage, plain pointers and sizes, caller-owned buffers; loadable with ctypes / cgo / JNI alike.
+ * Every entry point replaces one seam of the reference (friend1ws/nanomonsv v0.8.0, paths relative to the
+ * reference checkout):
+ *
+ *   nmsv_ssw_batch        <- parasail.ssw(s1, s2, open, extend, matrix)            count_sread_by_alignment.py:148-149
+ *                            (also post_proc.py:118-120, locate_bp_sbnd.py:28-29, generate_consensus.py:119)
+ *   nmsv_ssw_check_batch  <- ssw_check(query_fa, target_fa, use_ssw_lib)           count_sread_by_alignment.py:137-164
+ *                            (legacy twin long_read_validate.py:12-17,126-153)
+ *   nmsv_validate_batch   <- Alignment_counter.count_alignment_and_print[_sbnd]   count_sread_by_alignment.py:292-397
+ *                            i.e. the arithmetic of count_sread_by_alignment()     count_sread_by_alignment.py:401-451
+ *   nmsv_plan_* / nmsv_plan_run / nmsv_plan_download: the same stage split into upload / device-resident run /
+ *                            download so a caller (bench.py) can time the device step on its own.
+ *   The ctypes precedent in the reference is ssw_lib.CSsw (ssw_lib.py:95-199): unlike it, nothing returned by
+ *   this library has to be freed by the caller except the handles created by nmsv_create / nmsv_plan_create.
+ *
+ * Sequence encoding (all APIs): one byte per base; 0,1,2,3 = A,C,G,T (case folded by the caller), 4 = wildcard
+ * (any other byte; scores 0 against everything, like the extra row/column of parasail.matrix_create), see
+ * nmsv_encode_ascii.  All sequences of a call live in ONE buffer `codes`; sequence s occupies
+ * codes[offsets[s] .. offsets[s] + lens[s]).
+ *
+ * Error convention: every int function returns NMSV_OK (0) or a negative NMSV_E_* code; the message is available
+ * from nmsv_last_error(ctx).  There is no CPU fallback: without a usable CUDA device nmsv_create fails.
+ */
+#ifndef NMSV_H
+#define NMSV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMSV_ABI_VERSION 1
+
+#define NMSV_OK 0
+#define NMSV_E_INVALID (-1)   /* bad argument (NULL pointer, empty sequence, index out of range ...) */
+#define NMSV_E_CUDA (-2)      /* a CUDA runtime call failed */
+#define NMSV_E_RANGE (-3)     /* a score could exceed the 16-bit lanes (parasail would return NULL) */
+#define NMSV_E_CAPACITY (-4)  /* caller's record buffer too small; *n_records holds the required count */
+#define NMSV_E_INTERNAL (-5)  /* device-side consistency check failed */
+
+#define NMSV_NONE 0xFFFFFFFFu /* "no template in this slot" */
+#define NMSV_MAPQ_NONE (-1)   /* Python None in the seam TSV (count_sread_by_alignment.py:50,288) */
+
+#define NMSV_SLOT_VAR1 0
+#define NMSV_SLOT_VAR2 1
+#define NMSV_SLOT_REF1 2
+#define NMSV_SLOT_REF2 3
+
+/* nmsv_sv.flags */
+#define NMSV_SV_SHORT_DEL_DUP 1u /* is_short_del_dup: margin test against ref1 AND ref2 (:312-322,:336-341) */
+#define NMSV_SV_SBND 2u          /* single breakend: var1 only, margin against ref1, mapq1 only (:361-397) */
+
+typedef struct nmsv_ctx nmsv_ctx;
+typedef struct nmsv_plan nmsv_plan;
+
+typedef struct {
+    int32_t match;      /* parasail.matrix_create(alphabet, match, mismatch) */
+    int32_t mismatch;   /* <= 0 */
+    int32_t gap_open;   /* parasail.ssw(..., open, extend, ...): a gap of length k costs open + (k-1)*extend */
+    int32_t gap_extend; /* >= 0 */
+} nmsv_scoring;
+
+/* Result fields of parasail.ssw as read at count_sread_by_alignment.py:151-159 (0-based, inclusive).
+ * "read" = s1 (the template), "ref" = s2 (the long read).  score1 = -1: not representable in 16 bits. */
+typedef struct {
+    int32_t score1;
+    int32_t ref_begin1;
+    int32_t ref_end1;
+    int32_t read_begin1;
+    int32_t read_end1;
+} nmsv_ssw_result;
+
+/* One entry of the dict returned by ssw_check (:162): [score, qstart, qend, tstart, tend, strand], 1-based;
+ * q* = template coordinates, t* = read coordinates, strand +1 = '+', -1 = '-', 0 = slot absent / not computed. */
+typedef struct {
+    int32_t score;
+    int32_t qstart;
+    int32_t qend;
+    int32_t tstart;
+    int32_t tend;
+    int32_t strand;
+} nmsv_aln;
+
+/* One SV candidate (or single-breakend candidate) of a validation batch. The thresholds are the reference's
+ * double products turned into integer bounds BY THE CALLER with the reference's own float arithmetic:
+ *   score  >  ratio*len   <=>  score  >= score_min   (floor(x)+1)
+ *   qstart <  0.1*len     <=>  qstart <= qstart_max  (ceil(x)-1)
+ *   qend   >  0.9*len     <=>  qend   >= qend_min    (floor(x)+1)          (:327-333, :379-382)               */
+typedef struct {
+    uint32_t tmpl[4];       /* sequence index of var1, var2, ref1, ref2; NMSV_NONE = absent. Equal indices share work. */
+    uint32_t tmpl_rc[4];    /* NMSV_NONE: the engine derives the reverse complement (A<->T, C<->G, wildcard kept).
+                               Otherwise the index of an explicit my_seq.reverse_complement(template) sequence; needed
+                               only when the template holds lower-case acgt, which my_seq.py:20-26 leaves
+                               uncomplemented while parasail's mapper folds case.                              */
+    uint32_t read_begin;    /* reads[read_begin .. read_end) belong to this SV */
+    uint32_t read_end;
+    int32_t score_min[2];   /* for var1, var2 */
+    int32_t qstart_max[2];
+    int32_t qend_min[2];
+    int32_t margin;         /* var_ref_margin_thres (:171) */
+    int32_t min_mapq;       /* var_read_min_mapq */
+    uint32_t flags;         /* NMSV_SV_* */
+    uint32_t reserved;
+} nmsv_sv;
+
+typedef struct {
+    uint32_t seq;   /* sequence index of the read */
+    uint32_t sv;    /* index of its SV in the svs array */
+    int32_t mapq1;  /* NMSV_MAPQ_NONE = None */
+    int32_t mapq2;
+} nmsv_read;
+
+/* One supporting read: what count_alignment_and_print writes per line of sread_info (:352-358). */
+typedef struct {
+    uint32_t read;     /* index into the reads array */
+    uint32_t sv;
+    nmsv_aln aln[4];   /* var1, var2, ref1, ref2 (strand == 0 where the slot is absent) */
+} nmsv_record;
+
+/* Work/launch accounting of the last run of a plan (for GCUPS reporting). */
+typedef struct {
+    uint64_t cells_reference;  /* forward DP cells the reference would compute: sum n*m over every alignment */
+    uint64_t cells_executed;   /* forward DP cells actually computed on the device (identical templates shared) */
+    uint64_t cells_padded;     /* cells issued including row padding of the last tile and pipeline skew */
+    uint64_t fwd_tasks;        /* (read, template pair) wavefront tasks */
+    uint64_t rev_tasks;        /* begin-coordinate (reversed window) tasks */
+    uint32_t kernel_launches;  /* kernels launched by one nmsv_plan_run */
+    uint32_t n_classes;        /* row-strip classes (kernel instantiations) used */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t workspace_bytes;
+} nmsv_stats;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int nmsv_abi_version(void);
+int nmsv_create(nmsv_ctx **ctx, int device);          /* one ctx per process/GPU (mirrors --processes, run.py:367) */
+void nmsv_destroy(nmsv_ctx *ctx);
+const char *nmsv_last_error(const nmsv_ctx *ctx);     /* ctx may be NULL: error of a failed nmsv_create */
+int nmsv_set_stream(nmsv_ctx *ctx, void *cuda_stream); /* cudaStream_t to launch on (NULL = ctx's own stream) */
+int nmsv_device_info(const nmsv_ctx *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int64_t *l2_bytes,
+                     int64_t *global_mem_bytes, char *name, size_t name_len);
+
+/* byte -> code with the mapper of parasail.matrix_create("ACGT", ...): case-insensitive ACGT, rest wildcard */
+void nmsv_encode_ascii(const char *ascii, uint64_t n, uint8_t *codes);
+
+/* ---- operator seam: batched parasail.ssw ---------------------------------------------------------------------- */
+int nmsv_ssw_batch(nmsv_ctx *ctx, const uint8_t *codes, uint64_t n_codes, const uint64_t *offsets,
+                   const uint32_t *lens, uint32_t n_seqs, const uint32_t *tmpl_idx, const uint32_t *read_idx,
+                   uint64_t n_pairs, const nmsv_scoring *scoring, int want_begin, nmsv_ssw_result *out);
+
+/* ---- function seam: batched ssw_check (template and its reverse complement, strand rule, 1-based) ------------- */
+int nmsv_ssw_check_batch(nmsv_ctx *ctx, const uint8_t *codes, uint64_t n_codes, const uint64_t *offsets,
+                         const uint32_t *lens, uint32_t n_seqs, const uint32_t *tmpl_idx,
+                         const uint32_t *tmpl_rc_idx /* may be NULL; entries may be NMSV_NONE */,
+                         const uint32_t *read_idx, uint64_t n_pairs, const nmsv_scoring *scoring, nmsv_aln *out);
+
+/* ---- stage seam: supporting-read validation of a batch of SV candidates --------------------------------------- */
+/* One-shot, host buffers in / host buffers out (H2D + kernels + D2H inside). checked[i] / supporting[i] are the
+ * two trailing columns of the sread_count line of SV i; records (unordered) describe the supporting reads.      */
+int nmsv_validate_batch(nmsv_ctx *ctx, const uint8_t *codes, uint64_t n_codes, const uint64_t *offsets,
+                        const uint32_t *lens, uint32_t n_seqs, const nmsv_sv *svs, uint32_t n_svs,
+                        const nmsv_read *reads, uint32_t n_reads, const nmsv_scoring *scoring,
+                        int32_t *checked, int32_t *supporting, nmsv_record *records, uint64_t record_capacity,
+                        uint64_t *n_records);
+
+/* The same, split: nmsv_plan_create uploads and plans; nmsv_plan_run launches the whole device step on the
+ * ctx stream (asynchronous, inputs resident in HBM, no host synchronisation inside); nmsv_plan_download waits
+ * for the stream and copies results out.  A plan may be run any number of times.                              */
+int nmsv_plan_create(nmsv_ctx *ctx, nmsv_plan **plan, const uint8_t *codes, uint64_t n_codes,
+                     const uint64_t *offsets, const uint32_t *lens, uint32_t n_seqs, const nmsv_sv *svs,
+                     uint32_t n_svs, const nmsv_read *reads, uint32_t n_reads, const nmsv_scoring *scoring);
+int nmsv_plan_run(nmsv_plan *plan);
+int nmsv_plan_download(nmsv_plan *plan, int32_t *checked, int32_t *supporting, nmsv_record *records,
+                       uint64_t record_capacity, uint64_t *n_records);
+int nmsv_plan_stats(const nmsv_plan *plan, nmsv_stats *stats);
+/* per (read, slot) alignment tuples of the last run, reads*4 entries; begin coordinates (qstart for '+',
+ * qend for '-', tstart) are only filled for reads that reached the begin pass (debug / parity tests) */
+int nmsv_plan_download_alns(nmsv_plan *plan, nmsv_aln *alns, uint8_t *read_flags);
+void nmsv_plan_destroy(nmsv_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMSV_H */

@@ -1,0 +1,406 @@
+"""GPU-backed drop-in for nanomonsv/count_sread_by_alignment.py (reference v0.8.0).
+
+Same public names, argument meaning, output files and formats as the reference module, so `nanomonsv get` /
+`nanomonsv validate` (run.py:156-184, :501-511) can import this module instead:
+
+    gather_local_read_for_realignment   (:27-134)   host, pysam -- unchanged behaviour, writes the seam TSV
+    ssw_check                           (:137-164)  one template FASTA x reads FASTA -> dict, on the GPU
+    Alignment_counter                   (:167-397)  template construction + decision rules; alignment on the GPU
+    count_sread_by_alignment            (:401-451)  driver
+
+What changes is only WHERE the arithmetic runs: instead of 2-4 parasail.ssw calls per read, whole groups of SV
+candidates are packed into byte-coded batches and handed to libnmsv_sw.so (nmsv_validate_batch), which returns
+the per-SV counts and one record per supporting read.  The reference's float thresholds are converted to integer
+bounds here, with the same Python double arithmetic, before they go to the device.
+
+Quirks of the reference that change outputs are reproduced on purpose: var2 is always
+aligned; is_short_del_dup uses span + len(str(len(id))) < 300; the '+' single-breakend template carries the
+contig twice; strand ties go to '-'.
+"""
+from __future__ import annotations
+
+import math
+import os
+import random
+import subprocess
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .batch import BatchBuilder, integer_bounds  # noqa: F401
+from .engine import DEFAULT_SCORING, Engine, SeqPack, default_engine
+from .my_seq import needs_explicit_revcomp, reverse_complement
+
+# maximum number of read bases packed into one device batch (host memory / H2D granularity, not a GPU limit)
+BATCH_BASES = int(os.environ.get("NMSV_BATCH_BASES", str(512 << 20)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# read gathering (host, pysam) -- reference :12-134
+# ------------------------------------------------------------------------------------------------------------------
+def bam_subsample_fetch(alignment_h, tchr, tstart, tend, max_read_num=500):
+    """Reads overlapping a window; above max_read_num an (unseeded, like the reference) random subset."""
+    total = sum(1 for _ in alignment_h.fetch(tchr, tstart, tend))
+    keep = set(random.sample(range(total), min(max_read_num, total)))
+    for i, read in enumerate(alignment_h.fetch(tchr, tstart, tend)):
+        if i in keep:
+            yield read
+
+
+def _get_alignment_object(alignment_file, reference_fasta):
+    import pysam  # lazy: the GPU path itself does not need pysam
+    if alignment_file.endswith(".cram"):
+        return pysam.AlignmentFile(alignment_file, "rc", reference_filename=reference_fasta)
+    return pysam.AlignmentFile(alignment_file, "rb")
+
+
+def gather_local_read_for_realignment(sv_file, alignment_file, output_file, reference_fasta,
+                                      sbnd_file=None, output_file_sbnd=None, validate_sequence_length=200,
+                                      check_read_max_num=500, sort_option=None):
+    """Writes `key \\t qname \\t mapq1 \\t mapq2 \\t sequence` for every primary read near a breakpoint, sorted by
+    key with GNU sort (reference :27-134). check_read_max_num is accepted and, as in the reference, not forwarded."""
+    alignment_h = _get_alignment_object(alignment_file, reference_fasta)
+    rname2key: Dict[str, list] = {}
+    key2rname2mapq: Dict[str, dict] = {}
+    with open(sv_file) as hin:
+        for line in hin:
+            if line.startswith("#") or line.startswith("Chr_1"):
+                continue
+            F = line.rstrip("\n").split("\t")
+            key = f"{F[0]},{int(F[1])},{F[2]},{F[3]},{int(F[4])},{F[5]},{F[6]},{F[7]}"
+            per_key = key2rname2mapq.setdefault(key, {})
+            for which, (c, p) in enumerate(((F[0], int(F[1])), (F[3], int(F[4])))):
+                for read in bam_subsample_fetch(alignment_h, c, max(p - 100, 0), p + 100):
+                    rname2key.setdefault(read.qname, []).append(key)
+                    per_key.setdefault(read.qname, [None, None])[which] = read.mapping_quality
+    for rname in rname2key:
+        rname2key[rname] = list(set(rname2key[rname]))
+
+    rname2key_sbnd: Dict[str, list] = {}
+    key2rname2mapq_sbnd: Dict[str, dict] = {}
+    if sbnd_file is not None:
+        with open(sbnd_file) as hin:
+            for line in hin:
+                if line.startswith("#") or line.startswith("Chr_1"):
+                    continue
+                F = line.rstrip("\n").split("\t")
+                pos = int(F[1])
+                key = f"{F[0]},{pos},{F[2]},{F[3][:validate_sequence_length]},{F[4]}"
+                per_key = key2rname2mapq_sbnd.setdefault(key, {})
+                for read in bam_subsample_fetch(alignment_h, F[0], max(pos - 100, 0), pos + 100):
+                    rname2key_sbnd.setdefault(read.qname, []).append(key)
+                    per_key[read.qname] = read.mapping_quality
+        for rname in rname2key_sbnd:
+            rname2key_sbnd[rname] = list(set(rname2key_sbnd[rname]))
+
+    hout = open(output_file + ".tmp.unsorted", "w")
+    hout_sbnd = open(output_file_sbnd + ".tmp.unsorted", "w") if sbnd_file is not None else None
+    for read in alignment_h.fetch():
+        if read.is_supplementary or read.is_secondary or read.is_duplicate:
+            continue
+        in_main = read.qname in rname2key
+        in_sbnd = sbnd_file is not None and read.qname in rname2key_sbnd
+        if not (in_main or in_sbnd):
+            continue
+        read_seq = read.query_sequence
+        if read.is_reverse:
+            read_seq = reverse_complement(read_seq)
+        if in_main:
+            for key in rname2key[read.qname]:
+                mapq1, mapq2 = key2rname2mapq[key][read.qname]
+                print(f"{key}\t{read.qname}\t{mapq1}\t{mapq2}\t{read_seq}", file=hout)
+        if in_sbnd:
+            for key in rname2key_sbnd[read.qname]:
+                print(f"{key}\t{read.qname}\t{key2rname2mapq_sbnd[key][read.qname]}\tNone\t{read_seq}", file=hout_sbnd)
+    hout.close()
+    if hout_sbnd is not None:
+        hout_sbnd.close()
+
+    def gnu_sort(path):
+        with open(path, "w") as h:
+            subprocess.call(["sort", "-k1,1"] + sort_option.split(" ") + [path + ".tmp.unsorted"], stdout=h)
+        os.remove(path + ".tmp.unsorted")
+
+    gnu_sort(output_file)
+    if sbnd_file is not None:
+        gnu_sort(output_file_sbnd)
+    alignment_h.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# small parsers shared by ssw_check and the counter
+# ------------------------------------------------------------------------------------------------------------------
+def read_fasta(path: str):
+    """(id, sequence) records with the semantics of pyssw.read (pyssw.py:31-47): id = first token of the header,
+    lines concatenated and stripped, a record with an empty sequence is only emitted when it is the last one."""
+    sid, parts, have = "", [], False
+    with open(path) as f:
+        for line in f:
+            if line.startswith(">"):
+                seq = "".join(parts)
+                if seq:
+                    yield sid, seq
+                sid, parts, have = line.strip()[1:].split()[0], [], True
+            else:
+                parts.append(line.strip())
+    if have or parts:
+        yield sid, "".join(parts)
+
+
+def _aln_list(a) -> list:
+    """nmsv_aln -> the 6-element list of reference ssw_check (:162)."""
+    return [int(a["score"]), int(a["qstart"]), int(a["qend"]), int(a["tstart"]), int(a["tend"]),
+            "+" if a["strand"] > 0 else "-"]
+
+
+def ssw_check(query, target, use_ssw=False, engine: Optional[Engine] = None):
+    """Reference ssw_check (:137-164): the template(s) in FASTA `query` against every read of FASTA `target`, both
+    strands, keep '+' only if strictly better; returns {read id: [score, qstart, qend, tstart, tend, strand]}.
+    `use_ssw` is accepted and ignored, as in the reference."""
+    eng = engine or default_engine()
+    info: Dict[str, list] = {}
+    reads = list(read_fasta(target))
+    for _, tseq in read_fasta(query):
+        if not reads:
+            continue
+        pack = SeqPack()
+        t = pack.add(tseq)
+        rc = pack.add(reverse_complement(tseq)) if needs_explicit_revcomp(tseq) else _lib.NMSV_NONE
+        ridx = [pack.add(rseq) for _, rseq in reads]
+        res = eng.ssw_check_batch(pack, [t] * len(ridx), ridx, [rc] * len(ridx))
+        for (rid, _), a in zip(reads, res):
+            info[rid] = _aln_list(a)
+    return info
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# template construction and decision thresholds -- reference :207-283, :327-346
+# ------------------------------------------------------------------------------------------------------------------
+def canonical_templates(key: str, fasta, L: int = 200) -> Tuple[str, str, str, str, bool]:
+    """(variant_segment_1, variant_segment_2, reference_segment_1, reference_segment_2, is_short_del_dup)."""
+    chr1, pos1, dir1, chr2, pos2, dir2, inseq, sv_id = key.split(",")
+    pos1, pos2 = int(pos1), int(pos2)
+    # quirk (:210-223): the column compared against 300 is len(str(len(id))) (or len("0") when there is no
+    # insertion), not the insertion length
+    span_extra = len(str(len("" if inseq == "---" else sv_id)))
+    short = (chr1 == chr2 and (dir1, dir2) in (("+", "-"), ("-", "+")) and pos2 - pos1 + span_extra < 300)
+    ins = "" if inseq == "---" else inseq
+
+    def ref(c, a, b):
+        return fasta.fetch(c, max(a, 0), b).upper()
+
+    ref1 = ref(chr1, pos1 - L - 1, pos1 + L - 1)
+    ref2 = ref(chr2, pos2 - L - 1, pos2 + L - 1)
+    if dir1 == "+":
+        variant = ref(chr1, pos1 - L - 1, pos1 - 1) + ins
+    else:
+        variant = reverse_complement(fasta.fetch(chr1, pos1 - 1, pos1 + L - 1).upper()) + reverse_complement(ins)
+    if dir2 == "-":
+        variant += fasta.fetch(chr2, pos2 - 1, pos2 + L - 1).upper()
+    else:
+        variant += reverse_complement(ref(chr2, pos2 - L - 1, pos2 - 1))
+    n = min(2 * L, len(variant))
+    return variant[:n], variant[len(variant) - n:], ref1, ref2, short
+
+
+def sbnd_templates(key: str, fasta, L: int = 200) -> Tuple[str, str]:
+    """(variant_segment_1, reference_segment_1) of a single-breakend key `chr,pos,dir,contig,id` (:267-283)."""
+    chrom, pos, direction, contig, _ = key.split(",")
+    pos = int(pos)
+    ref1 = fasta.fetch(chrom, max(pos - L - 1, 0), pos + L - 1).upper()
+    if direction == "+":
+        head = fasta.fetch(chrom, max(pos - L - 1, 0), pos).upper() + contig   # the contig is appended here ...
+    else:
+        head = reverse_complement(fasta.fetch(chrom, pos - 1, pos + L - 1).upper())
+    return head + contig, ref1                                                 # ... and again here (:279,:283)
+
+
+@dataclass
+class SvJob:
+    key: str
+    is_sbnd: bool
+    templates: List[Optional[str]]           # var1, var2, ref1, ref2
+    short: bool
+    read_ids: List[str] = field(default_factory=list)
+    read_seqs: Dict[str, str] = field(default_factory=dict)     # id -> sequence (last record wins, like the dict in :162)
+    read_mapq: Dict[str, Tuple[Optional[int], Optional[int]]] = field(default_factory=dict)
+    bases: int = 0
+
+
+def _mapq(v) -> Optional[int]:
+    if v is None or v == "None":
+        return None
+    return int(v)
+
+
+class Alignment_counter(object):
+    """Same constructor and methods as the reference class (:167-397). SV candidates are queued and sent to the GPU in
+    batches; call flush() (or let count_sread_by_alignment do it) to write everything that is pending."""
+
+    def __init__(self, output_count_file, output_alignment_info_file, reference_fasta,
+                 var_read_min_mapq, score_ratio_thres, use_ssw_lib, debug, validate_sequence_length=200,
+                 start_pos_thres=0.1, end_pos_thres=0.9, var_ref_margin_thres=20, engine: Optional[Engine] = None,
+                 scoring=DEFAULT_SCORING):
+        self.temp_key = None
+        self.hout_count = open(output_count_file, "w")
+        self.hout_ainfo = open(output_alignment_info_file, "w")
+        if isinstance(reference_fasta, str):
+            import pysam  # lazy
+            self.reference_fasta_h = pysam.FastaFile(reference_fasta)
+        else:
+            self.reference_fasta_h = reference_fasta      # any object with fetch(chrom, start0, end0)
+        self.validate_sequence_length = validate_sequence_length
+        self.score_ratio_thres = score_ratio_thres
+        self.start_pos_thres = start_pos_thres
+        self.end_pos_thres = end_pos_thres
+        self.var_ref_margin_thres = var_ref_margin_thres
+        self.var_read_min_mapq = var_read_min_mapq
+        self.use_ssw_lib = use_ssw_lib          # accepted, ignored (reference :137)
+        self.debug = debug
+        self.scoring = scoring
+        self._engine = engine
+        self._job: Optional[SvJob] = None
+        self._queue: List[SvJob] = []
+        self._queued_bases = 0
+        self.batches_run = 0
+
+    # ---- reference-shaped interface
+    def initialize(self, key, is_sbnd=False):
+        self.temp_key = key
+        L = self.validate_sequence_length
+        if is_sbnd:
+            var1, ref1 = sbnd_templates(key, self.reference_fasta_h, L)
+            self._job = SvJob(key, True, [var1, None, ref1, None], False)
+        else:
+            var1, var2, ref1, ref2, short = canonical_templates(key, self.reference_fasta_h, L)
+            self._job = SvJob(key, False, [var1, var2, ref1 if short else None, ref2 if short else None], short)
+
+    def add_long_read_seq(self, treadid, tseq, tmapq1, tmapq2):
+        job = self._job
+        rid_tokens = treadid.split()
+        rid = rid_tokens[0] if rid_tokens else ""
+        seq = tseq.strip()
+        job.read_mapq[rid] = (_mapq(tmapq1), _mapq(tmapq2))
+        if not seq:
+            return          # pyssw.read drops records with an empty sequence (pyssw.py:39-40)
+        if rid not in job.read_seqs:
+            job.read_ids.append(rid)
+        else:
+            job.bases -= len(job.read_seqs[rid])
+        job.read_seqs[rid] = seq
+        job.bases += len(seq)
+
+    def count_alignment_and_print(self):
+        self._enqueue()
+
+    def count_alignment_and_print_sbnd(self):
+        self._enqueue()
+
+    def _enqueue(self):
+        if self._job is None:
+            return
+        self._queue.append(self._job)
+        self._queued_bases += self._job.bases
+        self._job = None
+        if self._queued_bases >= BATCH_BASES:
+            self.flush()
+
+    # ---- GPU batch
+    def flush(self):
+        if not self._queue:
+            return
+        eng = self._engine or default_engine()
+        bb = BatchBuilder(self.score_ratio_thres, self.start_pos_thres, self.end_pos_thres,
+                          self.var_ref_margin_thres, self.var_read_min_mapq)
+        for job in self._queue:
+            bb.add_sv(job.templates, job.is_sbnd, job.short)
+            for rid in job.read_ids:
+                m1, m2 = job.read_mapq.get(rid, (None, None))
+                bb.add_read(job.read_seqs[rid], m1, m2)
+        pack, svs, reads = bb.finalize()
+        checked, supporting, records = eng.validate(pack, svs, reads, self.scoring)
+        self.batches_run += 1
+
+        by_sv: Dict[int, list] = {}
+        for rec in records:
+            by_sv.setdefault(int(rec["sv"]), []).append(rec)
+        for i, job in enumerate(self._queue):
+            head = "\t".join(job.key.split(","))
+            print(f"{head}\t{int(checked[i])}\t{int(supporting[i])}", file=self.hout_count)
+            for rec in by_sv.get(i, []):
+                rid = job.read_ids[int(rec["read"]) - int(svs[i]["read_begin"])]
+                if job.is_sbnd:
+                    fields = _aln_list(rec["aln"][0])
+                else:
+                    fields = _aln_list(rec["aln"][0]) + _aln_list(rec["aln"][1])
+                    fields += (_aln_list(rec["aln"][2]) + _aln_list(rec["aln"][3])) if job.short else ["None"] * 12
+                print(f"{head}\t{rid}\t" + "\t".join(str(x) for x in fields), file=self.hout_ainfo)
+        self._queue = []
+        self._queued_bases = 0
+
+    def close(self):
+        self.flush()
+        for h in (self.hout_count, self.hout_ainfo):
+            if not h.closed:
+                h.close()
+        if hasattr(self.reference_fasta_h, "close"):
+            try:
+                self.reference_fasta_h.close()
+            except Exception:
+                pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _stream_seam(seam_file: str, counter: Alignment_counter, is_sbnd: bool) -> None:
+    """Group-by over the key-sorted seam TSV (reference :414-425 and :436-448)."""
+    with open(seam_file) as hin:
+        for line in hin:
+            tkey, treadid, tmapq1, tmapq2, tseq = line.rstrip("\n").split("\t")
+            if is_sbnd:
+                tmapq2 = "None"
+            if counter.temp_key != tkey:
+                if counter.temp_key is not None:
+                    counter.count_alignment_and_print_sbnd() if is_sbnd else counter.count_alignment_and_print()
+                counter.initialize(tkey, is_sbnd=is_sbnd)
+            counter.add_long_read_seq(treadid, tseq, tmapq1, tmapq2)
+        if counter.temp_key is not None:
+            counter.count_alignment_and_print_sbnd() if is_sbnd else counter.count_alignment_and_print()
+    counter.close()
+
+
+def count_sread_from_seam(seam_file, output_count_file, output_alignment_info_file, reference_fasta, is_sbnd=False,
+                          var_read_min_mapq=0, score_ratio_thres=1.2, debug=False, engine=None, **kwargs):
+    """The part of count_sread_by_alignment after read gathering: seam TSV -> sread_count / sread_info files."""
+    counter = Alignment_counter(output_count_file, output_alignment_info_file, reference_fasta, var_read_min_mapq,
+                                score_ratio_thres, False, debug, engine=engine, **kwargs)
+    _stream_seam(seam_file, counter, is_sbnd)
+    return counter
+
+
+def count_sread_by_alignment(sv_file, alignment_file, output_count_file, output_alignment_info_file, reference_fasta,
+                             sbnd_file=None, output_count_file_sbnd=None, output_alignment_info_file_sbnd=None,
+                             check_read_max_num=500, var_read_min_mapq=0, score_ratio_thres=1.2, use_ssw_lib=False,
+                             sort_option=None, debug=False, engine: Optional[Engine] = None):
+    """Same signature as the reference (:401-403) plus an optional engine handle."""
+    seam = output_count_file + ".tmp.local_read_for_realignment"
+    seam_sbnd = (output_count_file_sbnd + ".tmp.local_read_for_realignment") if output_count_file_sbnd is not None else None
+    gather_local_read_for_realignment(sv_file, alignment_file, seam, reference_fasta, sbnd_file=sbnd_file,
+                                      output_file_sbnd=seam_sbnd, check_read_max_num=check_read_max_num,
+                                      sort_option=sort_option)
+    count_sread_from_seam(seam, output_count_file, output_alignment_info_file, reference_fasta, False,
+                          var_read_min_mapq, score_ratio_thres, debug, engine)
+    if not debug:
+        os.remove(seam)
+    if sbnd_file is None:
+        return
+    count_sread_from_seam(seam_sbnd, output_count_file_sbnd, output_alignment_info_file_sbnd, reference_fasta, True,
+                          var_read_min_mapq, score_ratio_thres, debug, engine)
+    if not debug:
+        os.remove(seam_sbnd)

@@ -1,0 +1,990 @@
+// nmsv_api.cu -- C ABI (include/nmsv.h) and the small planning / decision kernels around the wavefront kernel.
+//
+// Device pipeline of one validation batch (nmsv_plan_run; everything asynchronous on one stream):
+//   plan_fwd_kernel      (read, slot) -> SwTask: template + its reverse complement against the whole read
+//   sw_wavefront_kernel  per strip class R: scores and end cells of both strands          [the hot kernel]
+//   decide_kernel        strand rule (count_sread_by_alignment.py:151-160), integer threshold / margin / mapq tests
+//                        (:327-346, :379-389); emits begin-pass tasks only for reads that can still be supporting
+//   sw_wavefront_kernel  per strip class R on the reversed, bounded windows: begin cells  (parasail src/ssw.c)
+//   final_kernel         1-based 6-tuples (:153-162), final supporting decision, per-SV atomic counts, records
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/nmsv.h"
+#include "nmsv_sw.cuh"
+
+using namespace nmsv;
+
+// ------------------------------------------------------------------------------------------------------------------
+// strip classes
+// ------------------------------------------------------------------------------------------------------------------
+static const int kClassR[] = {4, 8, 13, 16, 19};
+static const int kNumClasses = (int)(sizeof(kClassR) / sizeof(kClassR[0]));
+
+static int choose_class(uint32_t len)
+{
+    // fewest padded rows; ties -> taller strips (fewer tiles, fewer boundary round trips)
+    int best = -1;
+    uint64_t best_rows = ~0ull;
+    for (int c = 0; c < kNumClasses; ++c) {
+        uint64_t tile = 32ull * kClassR[c];
+        uint64_t rows = (len + tile - 1) / tile * tile;
+        if (rows <= best_rows) { best_rows = rows; best = c; }
+    }
+    return best;
+}
+
+static uint32_t tiles_of(uint32_t len, int cls)
+{
+    uint32_t tile = 32u * kClassR[cls];
+    return (len + tile - 1) / tile;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+struct nmsv_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop;
+    int sm_clock_khz = 0;
+    int blocks_per_sm[8] = {0};
+    mutable std::string error;
+};
+
+static int set_err(const nmsv_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, call)                                                                             \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return set_err((ctx), NMSV_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                           __FILE__, __LINE__);                                                         \
+    } while (0)
+
+template <int R>
+static cudaError_t setup_class(int* blocks_per_sm)
+{
+    const size_t smem = kWarpsPerBlock * warp_smem_bytes<R>();
+    cudaError_t e = cudaFuncSetAttribute(sw_wavefront_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sw_wavefront_kernel<R>, kWarpsPerBlock * 32, smem);
+}
+
+static cudaError_t setup_class_idx(int cls, int* bps)
+{
+    switch (kClassR[cls]) {
+    case 4: return setup_class<4>(bps);
+    case 8: return setup_class<8>(bps);
+    case 13: return setup_class<13>(bps);
+    case 16: return setup_class<16>(bps);
+    case 19: return setup_class<19>(bps);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int R>
+static void launch_class(const SwParams& p, int grid, cudaStream_t s)
+{
+    sw_wavefront_kernel<R><<<grid, kWarpsPerBlock * 32, kWarpsPerBlock * warp_smem_bytes<R>(), s>>>(p);
+}
+
+static void launch_class_idx(int cls, const SwParams& p, int grid, cudaStream_t s)
+{
+    switch (kClassR[cls]) {
+    case 4: launch_class<4>(p, grid, s); break;
+    case 8: launch_class<8>(p, grid, s); break;
+    case 13: launch_class<13>(p, grid, s); break;
+    case 16: launch_class<16>(p, grid, s); break;
+    case 19: launch_class<19>(p, grid, s); break;
+    }
+}
+
+extern "C" int nmsv_abi_version(void) { return NMSV_ABI_VERSION; }
+
+extern "C" const char* nmsv_last_error(const nmsv_ctx* ctx)
+{
+    return ctx ? ctx->error.c_str() : g_create_error.c_str();
+}
+
+extern "C" int nmsv_create(nmsv_ctx** out, int device)
+{
+    if (!out) return set_err(nullptr, NMSV_E_INVALID, "nmsv_create: ctx pointer is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return set_err(nullptr, NMSV_E_CUDA, "nmsv_create: no usable CUDA device (%s); there is no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return set_err(nullptr, NMSV_E_INVALID, "nmsv_create: device %d out of range [0,%d)", device, n);
+    nmsv_ctx* ctx = new (std::nothrow) nmsv_ctx();
+    if (!ctx) return set_err(nullptr, NMSV_E_INVALID, "nmsv_create: out of host memory");
+    ctx->device = device;
+#define CREATE_TRY(call)                                                                                       \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess) {                                                                              \
+            set_err(nullptr, NMSV_E_CUDA, "nmsv_create: %s failed: %s", #call, cudaGetErrorString(e__));       \
+            delete ctx;                                                                                        \
+            return NMSV_E_CUDA;                                                                                \
+        }                                                                                                      \
+    } while (0)
+    CREATE_TRY(cudaSetDevice(device));
+    CREATE_TRY(cudaGetDeviceProperties(&ctx->prop, device));
+    if (ctx->prop.major < 9) {
+        set_err(nullptr, NMSV_E_CUDA, "nmsv_create: device %s (sm_%d%d) has no DPX instructions; this library is built for sm_100a",
+                ctx->prop.name, ctx->prop.major, ctx->prop.minor);
+        delete ctx;
+        return NMSV_E_CUDA;
+    }
+    CREATE_TRY(cudaDeviceGetAttribute(&ctx->sm_clock_khz, cudaDevAttrClockRate, device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (int c = 0; c < kNumClasses; ++c) CREATE_TRY(setup_class_idx(c, &ctx->blocks_per_sm[c]));
+    {   // keep freed blocks cached in the stream-ordered pool: plans are created and destroyed per batch
+        cudaMemPool_t pool;
+        CREATE_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = ~0ull;
+        CREATE_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    }
+#undef CREATE_TRY
+    *out = ctx;
+    return NMSV_OK;
+}
+
+extern "C" void nmsv_destroy(nmsv_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
+    delete ctx;
+}
+
+extern "C" int nmsv_set_stream(nmsv_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return NMSV_E_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_device_info(const nmsv_ctx* ctx, int32_t* sm_count, int32_t* sm_clock_khz, int64_t* l2_bytes,
+                                int64_t* global_mem_bytes, char* name, size_t name_len)
+{
+    if (!ctx) return NMSV_E_INVALID;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (sm_clock_khz) *sm_clock_khz = ctx->sm_clock_khz;
+    if (l2_bytes) *l2_bytes = ctx->prop.l2CacheSize;
+    if (global_mem_bytes) *global_mem_bytes = (int64_t)ctx->prop.totalGlobalMem;
+    if (name && name_len) { strncpy(name, ctx->prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return NMSV_OK;
+}
+
+extern "C" void nmsv_encode_ascii(const char* ascii, uint64_t n, uint8_t* codes)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        uint8_t c;
+        switch (ascii[i]) {
+        case 'A': case 'a': c = 0; break;
+        case 'C': case 'c': c = 1; break;
+        case 'G': case 'g': c = 2; break;
+        case 'T': case 't': c = 3; break;
+        default: c = 4;
+        }
+        codes[i] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// device buffers (stream-ordered pool)
+// ------------------------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaError_t alloc(size_t n, cudaStream_t s)
+    {
+        release();
+        stream = s;
+        bytes = n ? n : 16;
+        cudaError_t e = cudaMallocAsync(&p, bytes, s);
+        if (e != cudaSuccess) { p = nullptr; bytes = 0; }
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeAsync(p, stream);
+        p = nullptr; bytes = 0;
+    }
+    ~DevBuf() { release(); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------------------------
+struct Sel { int32_t score, erow, ecol, strand; };   // chosen strand of one (read, slot)
+
+enum : uint32_t { kCntFwdQueue = 0, kCntRevQueue = 8, kCntRevTasks = 16, kCntRecords = 17, kCntStatus = 18, kCntTotal = 32 };
+enum : uint8_t { kReadCandidate = 1, kReadSupporting = 2 };
+
+__device__ __forceinline__ int alias_of(const nmsv_sv& sv, int s)
+{
+    for (int q = 0; q < s; ++q)
+        if (sv.tmpl[q] == sv.tmpl[s] && sv.tmpl_rc[q] == sv.tmpl_rc[s]) return q;
+    return s;
+}
+
+// thread per (rank, slot): rank = position of the read in the cost-sorted order
+__global__ void plan_fwd_kernel(const nmsv_sv* __restrict__ svs, const nmsv_read* __restrict__ reads,
+                                const uint32_t* __restrict__ order, const uint64_t* __restrict__ offsets,
+                                const uint32_t* __restrict__ lens, const uint8_t* __restrict__ seq_class,
+                                uint32_t n_reads, SwTask* __restrict__ tasks)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_reads * 4u) return;
+    const uint32_t r = order[i >> 2];
+    const int s = (int)(i & 3u);
+    const nmsv_read rd = reads[r];
+    const nmsv_sv sv = svs[rd.sv];
+    SwTask t;
+    memset(&t, 0, sizeof(t));
+    t.out = r * 4u + (uint32_t)s;
+    t.rclass = 0xffffffffu;
+    const uint32_t tm = sv.tmpl[s];
+    const bool sbnd_skip = (sv.flags & NMSV_SV_SBND) && (s == NMSV_SLOT_VAR2 || s == NMSV_SLOT_REF2);
+    if (tm != NMSV_NONE && !sbnd_skip && alias_of(sv, s) == s) {
+        const uint32_t m = lens[tm];
+        t.a_base = offsets[tm];
+        t.a_len = m;
+        const uint32_t rc = sv.tmpl_rc[s];
+        if (rc == NMSV_NONE) { t.b_base = offsets[tm] + m - 1; t.flags = kBRev | kBComp; }
+        else { t.b_base = offsets[rc]; }
+        t.b_len = m;
+        t.c_base = offsets[rd.seq];
+        t.ncols = lens[rd.seq];
+        t.rclass = (uint32_t)seq_class[tm];   // strip height R itself
+    }
+    tasks[i] = t;
+}
+
+struct DecideParams {
+    const nmsv_sv* svs; const nmsv_read* reads; const uint64_t* offsets; const uint32_t* lens;
+    const uint8_t* seq_class; uint32_t n_reads;
+    const SwResult* fwd; Sel* sel; uint8_t* read_flags;
+    SwTask* rev_tasks; uint32_t* counters;
+    int match, open, ext;
+};
+
+__device__ __forceinline__ bool slot_present(const nmsv_sv& sv, int s)
+{
+    if (sv.tmpl[s] == NMSV_NONE) return false;
+    if ((sv.flags & NMSV_SV_SBND) && (s == NMSV_SLOT_VAR2 || s == NMSV_SLOT_REF2)) return false;
+    return true;
+}
+
+// columns an alignment of `score` that uses `rows` rows can span at most: every column-only gap position costs at
+// least min(open, ext) (DESIGN.md "begin pass window")
+__device__ __forceinline__ uint32_t window_cols(int rows, int score, int ecol, int match, int open, int ext)
+{
+    const int cmin = open < ext ? open : ext;
+    long long w = (long long)ecol + 1;
+    if (cmin > 0) {
+        long long slack = ((long long)match * rows - score) / cmin;
+        if (slack < 0) slack = 0;
+        long long bound = (long long)rows + slack;
+        if (bound < w) w = bound;
+    }
+    return (uint32_t)w;
+}
+
+__device__ __forceinline__ void emit_rev_task(const DecideParams& p, uint32_t out, uint32_t tm, uint32_t rc,
+                                              uint32_t read_seq, const Sel& sl)
+{
+    const uint32_t m = p.lens[tm];
+    SwTask t;
+    memset(&t, 0, sizeof(t));
+    t.a_len = (uint32_t)sl.erow + 1u;
+    if (sl.strand > 0) { t.a_base = p.offsets[tm] + (uint64_t)sl.erow; t.flags = kARev; }               // reverse(T[0..e])
+    else if (rc == NMSV_NONE) { t.a_base = p.offsets[tm] + (uint64_t)(m - 1 - sl.erow); t.flags = kAComp; } // reverse(RC(T)[0..e])
+    else { t.a_base = p.offsets[rc] + (uint64_t)sl.erow; t.flags = kARev; }
+    t.b_len = 0;
+    t.c_base = p.offsets[read_seq] + (uint64_t)sl.ecol;
+    t.flags |= kCRev;
+    t.ncols = window_cols(sl.erow + 1, sl.score, sl.ecol, p.match, p.open, p.ext);
+    t.out = out;
+    t.rclass = (uint32_t)p.seq_class[tm];
+    const uint32_t idx = atomicAdd(&p.counters[kCntRevTasks], 1u);
+    p.rev_tasks[idx] = t;
+}
+
+__global__ void decide_kernel(const DecideParams p)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n_reads) return;
+    const nmsv_read rd = p.reads[r];
+    const nmsv_sv sv = p.svs[rd.sv];
+    Sel sl[4];
+    bool present[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        present[s] = slot_present(sv, s);
+        Sel x = {0, 0, 0, 0};
+        if (present[s]) {
+            const SwResult f = p.fwd[r * 4u + (uint32_t)alias_of(sv, s)];
+            if (f.score[0] > f.score[1]) { x.score = f.score[0]; x.erow = f.row[0]; x.ecol = f.col[0]; x.strand = 1; }
+            else { x.score = f.score[1]; x.erow = f.row[1]; x.ecol = f.col[1]; x.strand = -1; }   // ties -> '-'
+        }
+        sl[s] = x;
+        p.sel[r * 4u + s] = x;
+    }
+    const bool sbnd = sv.flags & NMSV_SV_SBND;
+    bool pass = false;
+    const int nvar = sbnd ? 1 : 2;
+    for (int v = 0; v < nvar; ++v) {
+        if (!present[v] || sl[v].score < sv.score_min[v]) continue;
+        const int m = (int)p.lens[sv.tmpl[v]];
+        if (sl[v].strand > 0) pass |= (sl[v].erow + 1 >= sv.qend_min[v]);        // qend   = read_end1 + 1
+        else pass |= (m - sl[v].erow <= sv.qstart_max[v]);                       // qstart = m - read_end1_r
+    }
+    if (sbnd) {
+        pass = pass && present[NMSV_SLOT_REF1] && sl[0].score >= sl[NMSV_SLOT_REF1].score + sv.margin;
+        pass = pass && rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq;
+    } else {
+        if (sv.flags & NMSV_SV_SHORT_DEL_DUP) {
+            const int r1 = sl[NMSV_SLOT_REF1].score + sv.margin, r2 = sl[NMSV_SLOT_REF2].score + sv.margin;
+            const bool ok1 = present[0] && sl[0].score >= r1 && sl[0].score >= r2;
+            const bool ok2 = present[1] && sl[1].score >= r1 && sl[1].score >= r2;
+            pass = pass && present[NMSV_SLOT_REF1] && present[NMSV_SLOT_REF2] && (ok1 || ok2);
+        }
+        pass = pass && rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq
+                    && rd.mapq2 != NMSV_MAPQ_NONE && rd.mapq2 >= sv.min_mapq;
+    }
+    p.read_flags[r] = pass ? kReadCandidate : 0;
+    if (!pass) return;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+        if (present[s] && alias_of(sv, s) == s && sl[s].score > 0)
+            emit_rev_task(p, r * 4u + (uint32_t)s, sv.tmpl[s], sv.tmpl_rc[s], rd.seq, sl[s]);
+}
+
+__device__ __forceinline__ nmsv_aln make_aln(const Sel& sl, int m, int brow, int bcol)
+{
+    nmsv_aln a;
+    a.score = sl.score;
+    a.strand = sl.strand;
+    if (sl.strand > 0) { a.qstart = brow + 1; a.qend = sl.erow + 1; }
+    else { a.qstart = m - sl.erow; a.qend = m - brow; }
+    a.tstart = bcol + 1;
+    a.tend = sl.ecol + 1;
+    return a;
+}
+
+struct FinalParams {
+    const nmsv_sv* svs; const nmsv_read* reads; const uint32_t* lens; uint32_t n_reads;
+    const Sel* sel; const SwResult* rev; uint8_t* read_flags; nmsv_aln* alns;
+    int32_t* supporting; nmsv_record* records; uint32_t record_capacity; uint32_t* counters;
+};
+
+__global__ void final_kernel(const FinalParams p)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n_reads) return;
+    const nmsv_read rd = p.reads[r];
+    const nmsv_sv sv = p.svs[rd.sv];
+    const bool cand = p.read_flags[r] & kReadCandidate;
+    nmsv_aln al[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        nmsv_aln a = {0, 0, 0, 0, 0, 0};
+        if (slot_present(sv, s)) {
+            const Sel sl = p.sel[r * 4u + s];
+            const int m = (int)p.lens[sv.tmpl[s]];
+            int brow = 0, bcol = 0;
+            if (cand && sl.score > 0) {
+                const SwResult rv = p.rev[r * 4u + (uint32_t)alias_of(sv, s)];
+                if (rv.score[0] != sl.score) atomicAdd(&p.counters[kCntStatus], 1u);   // window bound violated
+                brow = sl.erow - rv.row[0];
+                bcol = sl.ecol - rv.col[0];
+            }
+            a = make_aln(sl, m, brow, bcol);
+            if (!cand) {   // begin pass skipped: begin-derived fields are not available
+                if (sl.strand > 0) a.qstart = 0; else a.qend = 0;
+                a.tstart = 0;
+            }
+        }
+        al[s] = a;
+        p.alns[r * 4u + s] = a;
+    }
+    if (!cand) return;
+    bool supp = false;
+    const int nvar = (sv.flags & NMSV_SV_SBND) ? 1 : 2;
+    for (int v = 0; v < nvar; ++v)
+        if (al[v].strand != 0)
+            supp |= (al[v].score >= sv.score_min[v] && al[v].qstart <= sv.qstart_max[v] && al[v].qend >= sv.qend_min[v]);
+    if (!supp) return;
+    p.read_flags[r] = kReadCandidate | kReadSupporting;
+    atomicAdd(&p.supporting[rd.sv], 1);
+    const uint32_t idx = atomicAdd(&p.counters[kCntRecords], 1u);
+    if (idx < p.record_capacity) {
+        nmsv_record rec;
+        rec.read = r; rec.sv = rd.sv;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) rec.aln[s] = al[s];
+        p.records[idx] = rec;
+    }
+}
+
+// ---- pair API helpers ---------------------------------------------------------------------------------------------
+struct PairParams {
+    const uint64_t* offsets; const uint32_t* lens; const uint8_t* seq_class;
+    const uint32_t* tmpl_idx; const uint32_t* rc_idx; const uint32_t* read_idx; uint32_t n_pairs;
+    int both_strands;
+    const SwResult* fwd; Sel* sel; SwTask* rev_tasks; const SwResult* rev; uint32_t* counters;
+    nmsv_ssw_result* out_ssw; nmsv_aln* out_aln; int want_begin;
+    int match, open, ext;
+};
+
+__global__ void pair_plan_kernel(const PairParams p, SwTask* __restrict__ tasks)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_pairs) return;
+    const uint32_t tm = p.tmpl_idx[i], rs = p.read_idx[i];
+    const uint32_t m = p.lens[tm];
+    SwTask t;
+    memset(&t, 0, sizeof(t));
+    t.a_base = p.offsets[tm];
+    t.a_len = m;
+    if (p.both_strands) {
+        const uint32_t rc = p.rc_idx ? p.rc_idx[i] : NMSV_NONE;
+        if (rc == NMSV_NONE) { t.b_base = p.offsets[tm] + m - 1; t.flags = kBRev | kBComp; }
+        else t.b_base = p.offsets[rc];
+        t.b_len = m;
+    }
+    t.c_base = p.offsets[rs];
+    t.ncols = p.lens[rs];
+    t.out = i;
+    t.rclass = (uint32_t)p.seq_class[tm];
+    tasks[i] = t;
+}
+
+__global__ void pair_decide_kernel(const PairParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_pairs) return;
+    const SwResult f = p.fwd[i];
+    Sel x;
+    if (!p.both_strands || f.score[0] > f.score[1]) { x.score = f.score[0]; x.erow = f.row[0]; x.ecol = f.col[0]; x.strand = 1; }
+    else { x.score = f.score[1]; x.erow = f.row[1]; x.ecol = f.col[1]; x.strand = -1; }
+    p.sel[i] = x;
+    if (!p.want_begin || x.score <= 0) return;
+    DecideParams d;
+    d.offsets = p.offsets; d.lens = p.lens; d.seq_class = p.seq_class; d.rev_tasks = p.rev_tasks; d.counters = p.counters;
+    d.match = p.match; d.open = p.open; d.ext = p.ext;
+    emit_rev_task(d, i, p.tmpl_idx[i], p.rc_idx ? p.rc_idx[i] : NMSV_NONE, p.read_idx[i], x);
+}
+
+__global__ void pair_final_kernel(const PairParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_pairs) return;
+    const Sel x = p.sel[i];
+    int brow = 0, bcol = 0;
+    if (p.want_begin && x.score > 0) {
+        const SwResult rv = p.rev[i];
+        if (rv.score[0] != x.score) atomicAdd(&p.counters[kCntStatus], 1u);
+        brow = x.erow - rv.row[0];
+        bcol = x.ecol - rv.col[0];
+    }
+    if (p.out_ssw) {
+        nmsv_ssw_result o;
+        o.score1 = x.score; o.read_end1 = x.erow; o.ref_end1 = x.ecol;
+        o.read_begin1 = p.want_begin ? brow : -1;
+        o.ref_begin1 = p.want_begin ? bcol : -1;
+        p.out_ssw[i] = o;
+    }
+    if (p.out_aln) p.out_aln[i] = make_aln(x, (int)p.lens[p.tmpl_idx[i]], brow, bcol);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// shared host-side validation / upload of the sequence tables
+// ------------------------------------------------------------------------------------------------------------------
+struct SeqTables {
+    DevBuf codes, offsets, lens, seq_class;
+    std::vector<uint8_t> cls_host;      // strip height R per sequence (0 = never used as a template)
+    uint64_t h2d = 0;
+};
+
+static int check_scoring(nmsv_ctx* ctx, const nmsv_scoring* sc)
+{
+    if (!sc) return set_err(ctx, NMSV_E_INVALID, "scoring is NULL");
+    if (sc->match <= 0 || sc->mismatch > 0 || sc->gap_open < 0 || sc->gap_extend < 0)
+        return set_err(ctx, NMSV_E_INVALID, "scoring must have match > 0, mismatch <= 0, gap_open >= 0, gap_extend >= 0");
+    if (sc->gap_open + sc->gap_extend > 4096 || -sc->mismatch > 4096 || sc->match > 4096)
+        return set_err(ctx, NMSV_E_RANGE, "scoring parameters too large for 16-bit lanes");
+    return NMSV_OK;
+}
+
+static int check_seq_tables(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, const uint64_t* offsets,
+                            const uint32_t* lens, uint32_t n_seqs)
+{
+    if (!codes || !offsets || !lens) return set_err(ctx, NMSV_E_INVALID, "codes/offsets/lens must not be NULL");
+    for (uint32_t s = 0; s < n_seqs; ++s)
+        if (offsets[s] > n_codes || (uint64_t)lens[s] > n_codes - offsets[s])
+            return set_err(ctx, NMSV_E_INVALID, "sequence %u (offset %llu, len %u) lies outside the %llu-byte code buffer",
+                           s, (unsigned long long)offsets[s], lens[s], (unsigned long long)n_codes);
+    return NMSV_OK;
+}
+
+static int check_template(nmsv_ctx* ctx, uint32_t idx, const uint32_t* lens, uint32_t n_seqs, const nmsv_scoring* sc, const char* what)
+{
+    if (idx >= n_seqs) return set_err(ctx, NMSV_E_INVALID, "%s index %u out of range (n_seqs %u)", what, idx, n_seqs);
+    if (lens[idx] == 0) return set_err(ctx, NMSV_E_INVALID, "%s %u is empty", what, idx);
+    // parasail: NULL when any H exceeds INT16_MAX - max(matrix) - 1 ; H <= match * rows
+    if ((uint64_t)sc->match * lens[idx] + (uint64_t)(sc->gap_open + sc->gap_extend) > 32767u - (uint32_t)sc->match - 1u)
+        return set_err(ctx, NMSV_E_RANGE, "%s %u of length %u could score beyond the 16-bit range (parasail.ssw would return None)",
+                       what, idx, lens[idx]);
+    return NMSV_OK;
+}
+
+static int upload_seq_tables(nmsv_ctx* ctx, SeqTables& st, const uint8_t* codes, uint64_t n_codes,
+                             const uint64_t* offsets, const uint32_t* lens, uint32_t n_seqs)
+{
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, st.codes.alloc(n_codes, s));
+    CUDA_TRY(ctx, st.offsets.alloc(sizeof(uint64_t) * n_seqs, s));
+    CUDA_TRY(ctx, st.lens.alloc(sizeof(uint32_t) * n_seqs, s));
+    CUDA_TRY(ctx, st.seq_class.alloc(n_seqs, s));
+    if (n_codes) CUDA_TRY(ctx, cudaMemcpyAsync(st.codes.p, codes, n_codes, cudaMemcpyHostToDevice, s));
+    if (n_seqs) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(st.offsets.p, offsets, sizeof(uint64_t) * n_seqs, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(st.lens.p, lens, sizeof(uint32_t) * n_seqs, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(st.seq_class.p, st.cls_host.data(), n_seqs, cudaMemcpyHostToDevice, s));
+    }
+    st.h2d = n_codes + (uint64_t)n_seqs * (8 + 4 + 1);
+    return NMSV_OK;
+}
+
+static int grid_for(const nmsv_ctx* ctx, int cls)
+{
+    return ctx->prop.multiProcessorCount * std::max(1, ctx->blocks_per_sm[cls]);
+}
+
+static int max_grid_warps(const nmsv_ctx* ctx)
+{
+    int g = 0;
+    for (int c = 0; c < kNumClasses; ++c) g = std::max(g, grid_for(ctx, c));
+    return g * kWarpsPerBlock;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// validation plan
+// ------------------------------------------------------------------------------------------------------------------
+struct nmsv_plan {
+    nmsv_ctx* ctx = nullptr;
+    uint32_t n_seqs = 0, n_svs = 0, n_reads = 0;
+    nmsv_scoring sc{};
+    SeqTables st;
+    DevBuf svs, reads, order, tasks, fwd, rev_tasks, rev, sel, alns, flags, supporting, records, counters, bnd;
+    uint32_t bnd_stride = 1;
+    std::vector<int> classes;          // indices into kClassR that occur in this batch
+    std::vector<int32_t> checked;
+    nmsv_stats stats{};
+    bool ran = false;
+};
+
+extern "C" void nmsv_plan_destroy(nmsv_plan* plan)
+{
+    if (!plan) return;
+    cudaSetDevice(plan->ctx->device);
+    delete plan;
+}
+
+extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* codes, uint64_t n_codes,
+                                const uint64_t* offsets, const uint32_t* lens, uint32_t n_seqs, const nmsv_sv* svs,
+                                uint32_t n_svs, const nmsv_read* reads, uint32_t n_reads, const nmsv_scoring* scoring)
+{
+    if (!ctx) return NMSV_E_INVALID;
+    if (!out) return set_err(ctx, NMSV_E_INVALID, "plan pointer is NULL");
+    *out = nullptr;
+    int rc = check_scoring(ctx, scoring);
+    if (rc) return rc;
+    rc = check_seq_tables(ctx, codes, n_codes, offsets, lens, n_seqs);
+    if (rc) return rc;
+    if ((n_svs && !svs) || (n_reads && !reads)) return set_err(ctx, NMSV_E_INVALID, "svs/reads must not be NULL");
+    if (n_reads > 0x3fffffffu) return set_err(ctx, NMSV_E_INVALID, "too many reads in one batch (%u)", n_reads);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+
+    nmsv_plan* pl = new (std::nothrow) nmsv_plan();
+    if (!pl) return set_err(ctx, NMSV_E_INVALID, "out of host memory");
+    pl->ctx = ctx; pl->n_seqs = n_seqs; pl->n_svs = n_svs; pl->n_reads = n_reads; pl->sc = *scoring;
+    struct Guard { nmsv_plan* p; ~Guard() { if (p) nmsv_plan_destroy(p); } } guard{pl};
+
+    // ---- validate SVs, pick strip classes
+    pl->st.cls_host.assign(n_seqs, 0);
+    bool class_used[8] = {false};
+    pl->checked.assign(n_svs, 0);
+    for (uint32_t i = 0; i < n_svs; ++i) {
+        const nmsv_sv& sv = svs[i];
+        if (sv.read_begin > sv.read_end || sv.read_end > n_reads)
+            return set_err(ctx, NMSV_E_INVALID, "SV %u has an invalid read range [%u,%u)", i, sv.read_begin, sv.read_end);
+        pl->checked[i] = (int32_t)(sv.read_end - sv.read_begin);
+        for (int s = 0; s < 4; ++s) {
+            if (sv.tmpl[s] == NMSV_NONE) continue;
+            rc = check_template(ctx, sv.tmpl[s], lens, n_seqs, scoring, "template");
+            if (rc) return rc;
+            if (sv.tmpl_rc[s] != NMSV_NONE) {
+                rc = check_template(ctx, sv.tmpl_rc[s], lens, n_seqs, scoring, "reverse-complement template");
+                if (rc) return rc;
+                if (lens[sv.tmpl_rc[s]] != lens[sv.tmpl[s]])
+                    return set_err(ctx, NMSV_E_INVALID, "SV %u slot %d: explicit reverse complement has a different length", i, s);
+            }
+            const int c = choose_class(lens[sv.tmpl[s]]);
+            pl->st.cls_host[sv.tmpl[s]] = (uint8_t)kClassR[c];
+            class_used[c] = true;
+        }
+        if ((sv.flags & NMSV_SV_SBND) && (sv.tmpl[NMSV_SLOT_VAR1] == NMSV_NONE || sv.tmpl[NMSV_SLOT_REF1] == NMSV_NONE))
+            return set_err(ctx, NMSV_E_INVALID, "single-breakend SV %u needs var1 and ref1", i);
+        if ((sv.flags & NMSV_SV_SHORT_DEL_DUP) && !(sv.flags & NMSV_SV_SBND) &&
+            (sv.tmpl[NMSV_SLOT_REF1] == NMSV_NONE || sv.tmpl[NMSV_SLOT_REF2] == NMSV_NONE))
+            return set_err(ctx, NMSV_E_INVALID, "short del/dup SV %u needs ref1 and ref2", i);
+    }
+    for (int c = 0; c < kNumClasses; ++c) if (class_used[c]) pl->classes.push_back(c);
+
+    // ---- validate reads, cost-sort (longest first), work accounting
+    std::vector<uint64_t> cost(n_reads);
+    uint32_t max_cols_multi = 0;
+    nmsv_stats& stt = pl->stats;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        const nmsv_read& rd = reads[r];
+        if (rd.seq >= n_seqs || lens[rd.seq] == 0) return set_err(ctx, NMSV_E_INVALID, "read %u: sequence index %u invalid or empty", r, rd.seq);
+        if (rd.sv >= n_svs) return set_err(ctx, NMSV_E_INVALID, "read %u: SV index %u out of range", r, rd.sv);
+        const nmsv_sv& sv = svs[rd.sv];
+        if (r < sv.read_begin || r >= sv.read_end) return set_err(ctx, NMSV_E_INVALID, "read %u is outside the read range of its SV %u", r, rd.sv);
+        const uint64_t n = lens[rd.seq];
+        uint64_t c = 0;
+        for (int s = 0; s < 4; ++s) {
+            if (sv.tmpl[s] == NMSV_NONE) continue;
+            if ((sv.flags & NMSV_SV_SBND) && (s == NMSV_SLOT_VAR2 || s == NMSV_SLOT_REF2)) continue;
+            const uint64_t m = lens[sv.tmpl[s]];
+            stt.cells_reference += 2 * m * n;
+            bool alias = false;
+            for (int q = 0; q < s; ++q) alias |= (sv.tmpl[q] == sv.tmpl[s] && sv.tmpl_rc[q] == sv.tmpl_rc[s]);
+            if (alias) continue;
+            const int cls = choose_class((uint32_t)m);
+            const uint32_t nt = tiles_of((uint32_t)m, cls);
+            stt.cells_executed += 2 * m * n;
+            stt.cells_padded += 2ull * nt * 32 * kClassR[cls] * (n + 31);
+            stt.fwd_tasks += 1;
+            if (nt > 1) max_cols_multi = std::max<uint32_t>(max_cols_multi, (uint32_t)n);
+            c += m * n;
+        }
+        cost[r] = c;
+    }
+    std::vector<uint32_t> order(n_reads);
+    for (uint32_t r = 0; r < n_reads; ++r) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+
+    // ---- upload
+    cudaStream_t s = ctx->stream;
+    rc = upload_seq_tables(ctx, pl->st, codes, n_codes, offsets, lens, n_seqs);
+    if (rc) return rc;
+    CUDA_TRY(ctx, pl->svs.alloc(sizeof(nmsv_sv) * n_svs, s));
+    CUDA_TRY(ctx, pl->reads.alloc(sizeof(nmsv_read) * n_reads, s));
+    CUDA_TRY(ctx, pl->order.alloc(sizeof(uint32_t) * n_reads, s));
+    if (n_svs) CUDA_TRY(ctx, cudaMemcpyAsync(pl->svs.p, svs, sizeof(nmsv_sv) * n_svs, cudaMemcpyHostToDevice, s));
+    if (n_reads) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(pl->reads.p, reads, sizeof(nmsv_read) * n_reads, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(pl->order.p, order.data(), sizeof(uint32_t) * n_reads, cudaMemcpyHostToDevice, s));
+    }
+    stt.h2d_bytes = pl->st.h2d + sizeof(nmsv_sv) * (uint64_t)n_svs + (sizeof(nmsv_read) + 4) * (uint64_t)n_reads;
+
+    // ---- workspace
+    const uint64_t nslots = (uint64_t)n_reads * 4;
+    CUDA_TRY(ctx, pl->tasks.alloc(sizeof(SwTask) * nslots, s));
+    CUDA_TRY(ctx, pl->fwd.alloc(sizeof(SwResult) * nslots, s));
+    CUDA_TRY(ctx, pl->rev_tasks.alloc(sizeof(SwTask) * nslots, s));
+    CUDA_TRY(ctx, pl->rev.alloc(sizeof(SwResult) * nslots, s));
+    CUDA_TRY(ctx, pl->sel.alloc(sizeof(Sel) * nslots, s));
+    CUDA_TRY(ctx, pl->alns.alloc(sizeof(nmsv_aln) * nslots, s));
+    CUDA_TRY(ctx, pl->flags.alloc(n_reads, s));
+    CUDA_TRY(ctx, pl->supporting.alloc(sizeof(int32_t) * n_svs, s));
+    CUDA_TRY(ctx, pl->records.alloc(sizeof(nmsv_record) * (uint64_t)n_reads, s));
+    CUDA_TRY(ctx, pl->counters.alloc(sizeof(uint32_t) * kCntTotal, s));
+    pl->bnd_stride = max_cols_multi ? max_cols_multi : 1;
+    const uint64_t bnd_bytes = max_cols_multi ? (uint64_t)max_grid_warps(ctx) * 2 * pl->bnd_stride * sizeof(uint2) : 16;
+    CUDA_TRY(ctx, pl->bnd.alloc(bnd_bytes, s));
+    stt.workspace_bytes = pl->tasks.bytes + pl->fwd.bytes + pl->rev_tasks.bytes + pl->rev.bytes + pl->sel.bytes +
+                          pl->alns.bytes + pl->flags.bytes + pl->supporting.bytes + pl->records.bytes + pl->bnd.bytes;
+    stt.n_classes = (uint32_t)pl->classes.size();
+    stt.kernel_launches = 3 + 2 * stt.n_classes;
+    // the caller's host buffers may be reused as soon as we return
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    guard.p = nullptr;
+    *out = pl;
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_plan_run(nmsv_plan* pl)
+{
+    if (!pl) return NMSV_E_INVALID;
+    nmsv_ctx* ctx = pl->ctx;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint32_t n_reads = pl->n_reads;
+    CUDA_TRY(ctx, cudaMemsetAsync(pl->counters.p, 0, sizeof(uint32_t) * kCntTotal, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(pl->supporting.p, 0, pl->supporting.bytes, s));
+    pl->ran = true;
+    if (n_reads == 0) return NMSV_OK;
+    const int tpb = 128;
+    const uint32_t nslots = n_reads * 4u;
+
+    plan_fwd_kernel<<<(nslots + tpb - 1) / tpb, tpb, 0, s>>>(pl->svs.as<nmsv_sv>(), pl->reads.as<nmsv_read>(),
+        pl->order.as<uint32_t>(), pl->st.offsets.as<uint64_t>(), pl->st.lens.as<uint32_t>(), pl->st.seq_class.as<uint8_t>(),
+        n_reads, pl->tasks.as<SwTask>());
+
+    SwParams sp;
+    sp.codes = pl->st.codes.as<uint8_t>();
+    sp.bnd = pl->bnd.as<uint2>(); sp.bnd_stride = pl->bnd_stride;
+    sp.match = pl->sc.match; sp.mismatch = pl->sc.mismatch; sp.open = pl->sc.gap_open; sp.ext = pl->sc.gap_extend;
+
+    sp.tasks = pl->tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = nslots; sp.results = pl->fwd.as<SwResult>();
+    for (size_t i = 0; i < pl->classes.size(); ++i) {
+        sp.queue_head = pl->counters.as<uint32_t>() + kCntFwdQueue + i;
+        launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
+    }
+
+    DecideParams dp;
+    dp.svs = pl->svs.as<nmsv_sv>(); dp.reads = pl->reads.as<nmsv_read>(); dp.offsets = pl->st.offsets.as<uint64_t>();
+    dp.lens = pl->st.lens.as<uint32_t>(); dp.seq_class = pl->st.seq_class.as<uint8_t>(); dp.n_reads = n_reads;
+    dp.fwd = pl->fwd.as<SwResult>(); dp.sel = pl->sel.as<Sel>(); dp.read_flags = pl->flags.as<uint8_t>();
+    dp.rev_tasks = pl->rev_tasks.as<SwTask>(); dp.counters = pl->counters.as<uint32_t>();
+    dp.match = pl->sc.match; dp.open = pl->sc.gap_open; dp.ext = pl->sc.gap_extend;
+    decide_kernel<<<(n_reads + tpb - 1) / tpb, tpb, 0, s>>>(dp);
+
+    sp.tasks = pl->rev_tasks.as<SwTask>(); sp.n_tasks_dev = pl->counters.as<uint32_t>() + kCntRevTasks; sp.n_tasks = 0;
+    sp.results = pl->rev.as<SwResult>();
+    for (size_t i = 0; i < pl->classes.size(); ++i) {
+        sp.queue_head = pl->counters.as<uint32_t>() + kCntRevQueue + i;
+        launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
+    }
+
+    FinalParams fp;
+    fp.svs = dp.svs; fp.reads = dp.reads; fp.lens = dp.lens; fp.n_reads = n_reads; fp.sel = dp.sel;
+    fp.rev = pl->rev.as<SwResult>(); fp.read_flags = dp.read_flags; fp.alns = pl->alns.as<nmsv_aln>();
+    fp.supporting = pl->supporting.as<int32_t>(); fp.records = pl->records.as<nmsv_record>();
+    fp.record_capacity = n_reads; fp.counters = dp.counters;
+    final_kernel<<<(n_reads + tpb - 1) / tpb, tpb, 0, s>>>(fp);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_plan_download(nmsv_plan* pl, int32_t* checked, int32_t* supporting, nmsv_record* records,
+                                  uint64_t record_capacity, uint64_t* n_records)
+{
+    if (!pl) return NMSV_E_INVALID;
+    nmsv_ctx* ctx = pl->ctx;
+    if (!pl->ran) return set_err(ctx, NMSV_E_INVALID, "nmsv_plan_download before nmsv_plan_run");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    uint32_t cnt[kCntTotal];
+    CUDA_TRY(ctx, cudaMemcpyAsync(cnt, pl->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    if (supporting && pl->n_svs)
+        CUDA_TRY(ctx, cudaMemcpyAsync(supporting, pl->supporting.p, sizeof(int32_t) * pl->n_svs, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    pl->stats.rev_tasks = cnt[kCntRevTasks];
+    pl->stats.d2h_bytes = sizeof(cnt) + sizeof(int32_t) * (uint64_t)pl->n_svs;
+    if (cnt[kCntStatus])
+        return set_err(ctx, NMSV_E_INTERNAL, "%u begin-pass windows did not reproduce their forward score", cnt[kCntStatus]);
+    if (checked) for (uint32_t i = 0; i < pl->n_svs; ++i) checked[i] = pl->checked[i];
+    const uint64_t nrec = cnt[kCntRecords];
+    if (n_records) *n_records = nrec;
+    if (records) {
+        if (nrec > record_capacity)
+            return set_err(ctx, NMSV_E_CAPACITY, "record buffer holds %llu entries but %llu reads are supporting",
+                           (unsigned long long)record_capacity, (unsigned long long)nrec);
+        if (nrec) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(records, pl->records.p, sizeof(nmsv_record) * nrec, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(ctx, cudaStreamSynchronize(s));
+            pl->stats.d2h_bytes += sizeof(nmsv_record) * nrec;
+        }
+    }
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_plan_download_alns(nmsv_plan* pl, nmsv_aln* alns, uint8_t* read_flags)
+{
+    if (!pl) return NMSV_E_INVALID;
+    nmsv_ctx* ctx = pl->ctx;
+    if (!pl->ran) return set_err(ctx, NMSV_E_INVALID, "nmsv_plan_download_alns before nmsv_plan_run");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    if (alns && pl->n_reads)
+        CUDA_TRY(ctx, cudaMemcpyAsync(alns, pl->alns.p, sizeof(nmsv_aln) * 4ull * pl->n_reads, cudaMemcpyDeviceToHost, s));
+    if (read_flags && pl->n_reads)
+        CUDA_TRY(ctx, cudaMemcpyAsync(read_flags, pl->flags.p, pl->n_reads, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_plan_stats(const nmsv_plan* pl, nmsv_stats* stats)
+{
+    if (!pl || !stats) return NMSV_E_INVALID;
+    *stats = pl->stats;
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_validate_batch(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, const uint64_t* offsets,
+                                   const uint32_t* lens, uint32_t n_seqs, const nmsv_sv* svs, uint32_t n_svs,
+                                   const nmsv_read* reads, uint32_t n_reads, const nmsv_scoring* scoring,
+                                   int32_t* checked, int32_t* supporting, nmsv_record* records,
+                                   uint64_t record_capacity, uint64_t* n_records)
+{
+    nmsv_plan* pl = nullptr;
+    int rc = nmsv_plan_create(ctx, &pl, codes, n_codes, offsets, lens, n_seqs, svs, n_svs, reads, n_reads, scoring);
+    if (rc) return rc;
+    rc = nmsv_plan_run(pl);
+    if (!rc) rc = nmsv_plan_download(pl, checked, supporting, records, record_capacity, n_records);
+    nmsv_plan_destroy(pl);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// pair APIs (operator seam and function seam)
+// ------------------------------------------------------------------------------------------------------------------
+static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, const uint64_t* offsets,
+                     const uint32_t* lens, uint32_t n_seqs, const uint32_t* tmpl_idx, const uint32_t* rc_idx,
+                     const uint32_t* read_idx, uint64_t n_pairs64, const nmsv_scoring* sc, int both_strands,
+                     int want_begin, nmsv_ssw_result* out_ssw, nmsv_aln* out_aln)
+{
+    if (!ctx) return NMSV_E_INVALID;
+    int rc = check_scoring(ctx, sc);
+    if (rc) return rc;
+    rc = check_seq_tables(ctx, codes, n_codes, offsets, lens, n_seqs);
+    if (rc) return rc;
+    if (n_pairs64 == 0) return NMSV_OK;
+    if (!tmpl_idx || !read_idx || (!out_ssw && !out_aln)) return set_err(ctx, NMSV_E_INVALID, "pair index / output arrays must not be NULL");
+    if (n_pairs64 > 0x7fffffffu) return set_err(ctx, NMSV_E_INVALID, "too many pairs in one call");
+    const uint32_t n_pairs = (uint32_t)n_pairs64;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+
+    SeqTables st;
+    st.cls_host.assign(n_seqs, 0);
+    bool class_used[8] = {false};
+    uint32_t max_cols_multi = 0;
+    for (uint32_t i = 0; i < n_pairs; ++i) {
+        rc = check_template(ctx, tmpl_idx[i], lens, n_seqs, sc, "template");
+        if (rc) return rc;
+        if (rc_idx && rc_idx[i] != NMSV_NONE) {
+            rc = check_template(ctx, rc_idx[i], lens, n_seqs, sc, "reverse-complement template");
+            if (rc) return rc;
+            if (lens[rc_idx[i]] != lens[tmpl_idx[i]]) return set_err(ctx, NMSV_E_INVALID, "pair %u: explicit reverse complement has a different length", i);
+        }
+        if (read_idx[i] >= n_seqs || lens[read_idx[i]] == 0) return set_err(ctx, NMSV_E_INVALID, "pair %u: read index %u invalid or empty", i, read_idx[i]);
+        const int c = choose_class(lens[tmpl_idx[i]]);
+        st.cls_host[tmpl_idx[i]] = (uint8_t)kClassR[c];
+        class_used[c] = true;
+        if (tiles_of(lens[tmpl_idx[i]], c) > 1) max_cols_multi = std::max(max_cols_multi, lens[read_idx[i]]);
+    }
+    std::vector<int> classes;
+    for (int c = 0; c < kNumClasses; ++c) if (class_used[c]) classes.push_back(c);
+
+    cudaStream_t s = ctx->stream;
+    rc = upload_seq_tables(ctx, st, codes, n_codes, offsets, lens, n_seqs);
+    if (rc) return rc;
+    DevBuf d_t, d_rc, d_r, tasks, fwd, rev_tasks, rev, sel, counters, bnd, d_out;
+    CUDA_TRY(ctx, d_t.alloc(4ull * n_pairs, s));
+    CUDA_TRY(ctx, d_r.alloc(4ull * n_pairs, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_t.p, tmpl_idx, 4ull * n_pairs, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_r.p, read_idx, 4ull * n_pairs, cudaMemcpyHostToDevice, s));
+    if (rc_idx) {
+        CUDA_TRY(ctx, d_rc.alloc(4ull * n_pairs, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_rc.p, rc_idx, 4ull * n_pairs, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(ctx, tasks.alloc(sizeof(SwTask) * (uint64_t)n_pairs, s));
+    CUDA_TRY(ctx, fwd.alloc(sizeof(SwResult) * (uint64_t)n_pairs, s));
+    CUDA_TRY(ctx, rev_tasks.alloc(sizeof(SwTask) * (uint64_t)n_pairs, s));
+    CUDA_TRY(ctx, rev.alloc(sizeof(SwResult) * (uint64_t)n_pairs, s));
+    CUDA_TRY(ctx, sel.alloc(sizeof(Sel) * (uint64_t)n_pairs, s));
+    CUDA_TRY(ctx, counters.alloc(sizeof(uint32_t) * kCntTotal, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(counters.p, 0, sizeof(uint32_t) * kCntTotal, s));
+    const uint32_t stride = max_cols_multi ? max_cols_multi : 1;
+    CUDA_TRY(ctx, bnd.alloc(max_cols_multi ? (uint64_t)max_grid_warps(ctx) * 2 * stride * sizeof(uint2) : 16, s));
+    const size_t out_bytes = out_ssw ? sizeof(nmsv_ssw_result) * (size_t)n_pairs : sizeof(nmsv_aln) * (size_t)n_pairs;
+    CUDA_TRY(ctx, d_out.alloc(out_bytes, s));
+
+    PairParams pp;
+    pp.offsets = st.offsets.as<uint64_t>(); pp.lens = st.lens.as<uint32_t>(); pp.seq_class = st.seq_class.as<uint8_t>();
+    pp.tmpl_idx = d_t.as<uint32_t>(); pp.rc_idx = rc_idx ? d_rc.as<uint32_t>() : nullptr; pp.read_idx = d_r.as<uint32_t>();
+    pp.n_pairs = n_pairs; pp.both_strands = both_strands;
+    pp.fwd = fwd.as<SwResult>(); pp.sel = sel.as<Sel>(); pp.rev_tasks = rev_tasks.as<SwTask>(); pp.rev = rev.as<SwResult>();
+    pp.counters = counters.as<uint32_t>();
+    pp.out_ssw = out_ssw ? d_out.as<nmsv_ssw_result>() : nullptr;
+    pp.out_aln = out_ssw ? nullptr : d_out.as<nmsv_aln>();
+    pp.want_begin = want_begin; pp.match = sc->match; pp.open = sc->gap_open; pp.ext = sc->gap_extend;
+
+    const int tpb = 128;
+    const int nb = (int)((n_pairs + tpb - 1) / tpb);
+    pair_plan_kernel<<<nb, tpb, 0, s>>>(pp, tasks.as<SwTask>());
+    SwParams sp;
+    sp.codes = st.codes.as<uint8_t>(); sp.bnd = bnd.as<uint2>(); sp.bnd_stride = stride;
+    sp.match = sc->match; sp.mismatch = sc->mismatch; sp.open = sc->gap_open; sp.ext = sc->gap_extend;
+    sp.tasks = tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = n_pairs; sp.results = fwd.as<SwResult>();
+    for (size_t i = 0; i < classes.size(); ++i) {
+        sp.queue_head = counters.as<uint32_t>() + kCntFwdQueue + i;
+        launch_class_idx(classes[i], sp, grid_for(ctx, classes[i]), s);
+    }
+    pair_decide_kernel<<<nb, tpb, 0, s>>>(pp);
+    if (want_begin) {
+        sp.tasks = rev_tasks.as<SwTask>(); sp.n_tasks_dev = counters.as<uint32_t>() + kCntRevTasks; sp.n_tasks = 0;
+        sp.results = rev.as<SwResult>();
+        for (size_t i = 0; i < classes.size(); ++i) {
+            sp.queue_head = counters.as<uint32_t>() + kCntRevQueue + i;
+            launch_class_idx(classes[i], sp, grid_for(ctx, classes[i]), s);
+        }
+    }
+    pair_final_kernel<<<nb, tpb, 0, s>>>(pp);
+    CUDA_TRY(ctx, cudaGetLastError());
+    uint32_t cnt[kCntTotal];
+    CUDA_TRY(ctx, cudaMemcpyAsync(cnt, counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_ssw ? (void*)out_ssw : (void*)out_aln, d_out.p, out_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (cnt[kCntStatus])
+        return set_err(ctx, NMSV_E_INTERNAL, "%u begin-pass windows did not reproduce their forward score", cnt[kCntStatus]);
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_ssw_batch(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, const uint64_t* offsets,
+                              const uint32_t* lens, uint32_t n_seqs, const uint32_t* tmpl_idx, const uint32_t* read_idx,
+                              uint64_t n_pairs, const nmsv_scoring* scoring, int want_begin, nmsv_ssw_result* out)
+{
+    return run_pairs(ctx, codes, n_codes, offsets, lens, n_seqs, tmpl_idx, nullptr, read_idx, n_pairs, scoring, 0,
+                     want_begin, out, nullptr);
+}
+
+extern "C" int nmsv_ssw_check_batch(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, const uint64_t* offsets,
+                                    const uint32_t* lens, uint32_t n_seqs, const uint32_t* tmpl_idx,
+                                    const uint32_t* tmpl_rc_idx, const uint32_t* read_idx, uint64_t n_pairs,
+                                    const nmsv_scoring* scoring, nmsv_aln* out)
+{
+    return run_pairs(ctx, codes, n_codes, offsets, lens, n_seqs, tmpl_idx, tmpl_rc_idx, read_idx, n_pairs, scoring, 1,
+                     1, nullptr, out);
+}

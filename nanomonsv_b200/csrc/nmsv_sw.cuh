@@ -1,0 +1,282 @@
+// nmsv_sw.cuh -- the Smith-Waterman wavefront kernel (sm_100a, DPX s16x2).
+//
+// Replaces the arithmetic of parasail.ssw as called at reference count_sread_by_alignment.py:148-149
+// (Gotoh affine-gap local alignment; end cell = first column reaching the maximum, then smallest row).
+//
+// Mapping (DESIGN.md "Kernel 1"):
+//   * one warp = one task = (row sequence A, row sequence B) x one column sequence.  A and B live in the low /
+//     high 16-bit half of every register, so one DPX instruction advances two independent alignments that share
+//     the read column: the template and its reverse complement (hot path), or A alone (begin pass).
+//   * rows are cut into tiles of 32*R; inside a tile lane l owns the R consecutive rows l*R .. l*R+R-1 and keeps
+//     their H (previous column) and E in registers.  Lane l works on column t-l at step t (anti-diagonal
+//     wavefront); H and F of a strip's last row go to lane l+1 with two __shfl_up_sync per step.
+//   * the substitution scores come from a per-warp shared-memory profile prof[code][row] (LDS.128, conflict
+//     free) so the inner loop has no compares; the read is staged through a shared-memory ring.
+//   * templates longer than one tile run tile after tile; the H/F row between two tiles goes through a per-warp
+//     global scratch that stays L2 resident (8 B per column).
+//   * all values carry the bias a = open+ext so that E-ext and F-ext are plain 32-bit adds (no borrow between
+//     the halves): they issue on the FMA pipe (IMAD.IADD) while the 4.5 DPX instructions per packed cell pair
+//     (VIADDMNMX.S16x2 x3, VIMNMX3.S16x2 x1.5) own the ALU pipe.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nmsv {
+
+constexpr int kPadCode = 5;        // column / row code that can never start or extend an alignment
+constexpr int kRowPad = 6;         // row beyond the end of a template half
+constexpr int kNumCodes = 6;       // A C G T wildcard pad
+constexpr int kPadScore = -128;
+constexpr int kChunk = 128;        // columns staged per refill
+constexpr int kWarpsPerBlock = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+enum : uint32_t { kARev = 1u, kAComp = 2u, kBRev = 4u, kBComp = 8u, kCRev = 16u };
+
+struct SwTask {          // 48 bytes
+    uint64_t a_base;     // index into codes of row 0 of half A (row i is a_base +/- i)
+    uint64_t b_base;
+    uint64_t c_base;     // index of column 0 (column j is c_base +/- j)
+    uint32_t a_len;      // rows of half A (0 = unused half)
+    uint32_t b_len;
+    uint32_t ncols;      // 0 = empty task
+    uint32_t flags;
+    uint32_t out;        // index into results
+    uint32_t rclass;     // strip height R of the kernel instantiation that owns this task
+};
+
+struct SwResult {        // [0] = half A, [1] = half B ; row/col 0-based in the task's own orientation
+    int32_t score[2];
+    int32_t row[2];
+    int32_t col[2];
+};
+
+struct SwParams {
+    const uint8_t* codes;
+    const SwTask* tasks;
+    const uint32_t* n_tasks_dev;   // when non-null the task count is read from device memory
+    uint32_t n_tasks;
+    uint32_t* queue_head;          // zeroed before the launch
+    SwResult* results;
+    uint2* bnd;                    // [grid warps][2][bnd_stride] tile-boundary scratch
+    uint32_t bnd_stride;
+    int match, mismatch, open, ext;
+};
+
+template <int R>
+__host__ __device__ constexpr int groups_of() { return (R + 3) / 4; }
+
+template <int R>
+__host__ __device__ constexpr size_t warp_smem_bytes()
+{
+    return (size_t)kNumCodes * groups_of<R>() * 32 * 16   // profile, uint4 [code][group][lane]
+         + (size_t)kChunk * 8                               // boundary ring, uint2 per column
+         + (size_t)2 * kChunk;                              // read ring, 1 byte per column
+}
+
+__device__ __forceinline__ uint32_t pack16(int lo, int hi)
+{
+    return ((uint32_t)hi << 16) | ((uint32_t)lo & 0xffffu);
+}
+
+__device__ __forceinline__ int fetch_code(const uint8_t* __restrict__ codes, uint64_t base, int i, bool rev, bool comp)
+{
+    int c = codes[rev ? base - (uint64_t)i : base + (uint64_t)i];
+    if (comp && c < 4) c = 3 - c;
+    return c;
+}
+
+__device__ __forceinline__ int sub_score(int rc, int b, int match, int mismatch)
+{
+    if (rc == kRowPad || b == kPadCode) return kPadScore;
+    if (rc > 3 || b > 3) return 0;
+    return rc == b ? match : mismatch;
+}
+
+// lexicographic "better": higher score, then smaller column, then smaller row
+__device__ __forceinline__ void warp_argbest(int& s, int& c, int& r)
+{
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        int os = __shfl_xor_sync(kFull, s, off);
+        int oc = __shfl_xor_sync(kFull, c, off);
+        int orw = __shfl_xor_sync(kFull, r, off);
+        bool take = (os > s) || (os == s && (oc < c || (oc == c && orw < r)));
+        if (take) { s = os; c = oc; r = orw; }
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (R <= 16 ? 4 : 3))
+sw_wavefront_kernel(const SwParams p)
+{
+    constexpr int G = groups_of<R>();
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    uint8_t* wbase = smem_raw + (size_t)warp * warp_smem_bytes<R>();
+    uint4* prof = reinterpret_cast<uint4*>(wbase);
+    uint2* bring = reinterpret_cast<uint2*>(wbase + (size_t)kNumCodes * G * 32 * 16);
+    uint8_t* rring = reinterpret_cast<uint8_t*>(bring + kChunk);
+    const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + warp;
+    uint2* const bnd0 = p.bnd + (size_t)gwarp * 2 * p.bnd_stride;
+
+    const uint32_t n_tasks = p.n_tasks_dev ? *p.n_tasks_dev : p.n_tasks;
+    const int bias = p.open + p.ext;
+    const uint32_t FLOOR = pack16(bias, bias);
+    const uint32_t NEG_OPEN = pack16(-p.open, -p.open);
+    const uint32_t NEG_EXT_ADD = (uint32_t)(-(p.ext * 65537));   // plain 32-bit add; no borrow because lo >= ext
+    const uint32_t EF_INIT = pack16(bias - p.open, bias - p.open);  // E = F = -open
+
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(p.queue_head, 1u);
+        ti = __shfl_sync(kFull, ti, 0);
+        if (ti >= n_tasks) break;
+        const SwTask task = p.tasks[ti];
+        if (task.rclass != (uint32_t)R || task.ncols == 0) continue;
+
+        const int a_len = (int)task.a_len, b_len = (int)task.b_len, ncols = (int)task.ncols;
+        const bool a_rev = task.flags & kARev, a_comp = task.flags & kAComp;
+        const bool b_rev = task.flags & kBRev, b_comp = task.flags & kBComp;
+        const bool c_rev = task.flags & kCRev;
+        const int rows = a_len > b_len ? a_len : b_len;
+        const int ntiles = (rows + 32 * R - 1) / (32 * R);
+        const int total_steps = ncols + 31;
+
+        // running best over tiles, per half: {score, col, row}
+        int bs0 = 0, bc0 = 0, br0 = a_len - 1;
+        int bs1 = 0, bc1 = 0, br1 = b_len - 1;
+
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const int row0 = tile * 32 * R + lane * R;
+            uint2* const bnd_in = bnd0 + (size_t)((tile + 1) & 1) * p.bnd_stride;
+            uint2* const bnd_out = bnd0 + (size_t)(tile & 1) * p.bnd_stride;
+            const bool write_bnd = (tile + 1 < ntiles);
+
+            __syncwarp();
+            // ---- profile of this tile: prof[code][group][lane].{x,y,z,w} = (S_A | S_B << 16) of row 4*group+w
+            {
+                uint32_t* pw = reinterpret_cast<uint32_t*>(prof);
+                for (int k = 0; k < 4 * G; ++k) {
+                    const int row = row0 + k;
+                    const int ca = (k < R && row < a_len) ? fetch_code(p.codes, task.a_base, row, a_rev, a_comp) : kRowPad;
+                    const int cb = (k < R && row < b_len) ? fetch_code(p.codes, task.b_base, row, b_rev, b_comp) : kRowPad;
+#pragma unroll
+                    for (int b = 0; b < kNumCodes; ++b) {
+                        const uint32_t w = pack16(sub_score(ca, b, p.match, p.mismatch), sub_score(cb, b, p.match, p.mismatch));
+                        pw[(((b * G) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = w;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < (2 * kChunk) / 32; ++u) rring[u * 32 + lane] = (uint8_t)kPadCode;
+            }
+
+            uint32_t Hold[R], E[R];
+#pragma unroll
+            for (int k = 0; k < R; ++k) { Hold[k] = FLOOR; E[k] = EF_INIT; }
+            uint32_t best = FLOOR, bestprev = FLOOR;
+            int col_lo = 0, row_lo = 0, col_hi = 0, row_hi = 0;   // only meaningful once best rose above FLOOR
+            uint32_t h_last = FLOOR, f_out = EF_INIT, diag = FLOOR;
+            int jj = -lane - 1;
+
+            for (int t0 = 0; t0 < total_steps; t0 += kChunk) {
+                // ---- refill: columns [t0, t0+kChunk) of the read ring and of the boundary ring
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < kChunk / 32; ++u) {
+                    const int col = t0 + u * 32 + lane;
+                    uint8_t c = (uint8_t)kPadCode;
+                    uint2 bv = make_uint2(FLOOR, EF_INIT);
+                    if (col < ncols) {
+                        c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
+                        if (tile > 0) bv = __ldcg(bnd_in + col);
+                    }
+                    rring[col & (2 * kChunk - 1)] = c;
+                    bring[col & (kChunk - 1)] = bv;
+                }
+                __syncwarp();
+
+                const int t1 = (t0 + kChunk < total_steps) ? t0 + kChunk : total_steps;
+                for (int t = t0; t < t1; ++t) {
+                    ++jj;   // jj == t - lane : the column this lane works on
+                    uint32_t hin = __shfl_up_sync(kFull, h_last, 1);
+                    uint32_t fin = __shfl_up_sync(kFull, f_out, 1);
+                    const uint2 bv = bring[t & (kChunk - 1)];
+                    if (lane == 0) { hin = bv.x; fin = bv.y; }
+                    const uint32_t b = rring[jj & (2 * kChunk - 1)];
+                    const uint4* pp = prof + b * (G * 32) + lane;
+
+                    uint32_t S[4 * G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const uint4 v = pp[g * 32];
+                        S[4 * g + 0] = v.x; S[4 * g + 1] = v.y; S[4 * g + 2] = v.z; S[4 * g + 3] = v.w;
+                    }
+
+                    uint32_t hd = diag;
+                    diag = hin;
+                    uint32_t F = fin;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) {
+                        const uint32_t x = __viaddmax_s16x2(hd, S[k], E[k]);        // max(Hdiag + S, E)
+                        const uint32_t h = __vimax3_s16x2(x, F, FLOOR);             // H = max(., F, 0)
+                        const uint32_t ed = E[k] + NEG_EXT_ADD;                     // E - ext   (FMA pipe)
+                        const uint32_t fd = F + NEG_EXT_ADD;                        // F - ext   (FMA pipe)
+                        E[k] = __viaddmax_s16x2(h, NEG_OPEN, ed);                   // E' = max(H - open, E - ext)
+                        F = __viaddmax_s16x2(h, NEG_OPEN, fd);                      // F' for the next row
+                        hd = Hold[k];
+                        Hold[k] = h;
+                    }
+#pragma unroll
+                    for (int k = 0; k + 1 < R; k += 2) best = __vimax3_s16x2(best, Hold[k], Hold[k + 1]);
+                    if (R & 1) best = __vimax3_s16x2(best, Hold[R - 1], Hold[R - 1]);
+                    h_last = Hold[R - 1];
+                    f_out = F;
+
+                    if (write_bnd && lane == 31 && (unsigned)jj < (unsigned)ncols)
+                        __stcg(bnd_out + jj, make_uint2(h_last, f_out));
+
+                    if (best != bestprev) {
+                        // rare: this lane's running maximum rose in this column -> remember column and first row
+                        const uint32_t changed = best ^ bestprev;
+                        if (changed & 0xffffu) {
+                            col_lo = jj;
+                            int r = R - 1;
+#pragma unroll
+                            for (int k = R - 1; k >= 0; --k) if (((Hold[k] ^ best) & 0xffffu) == 0) r = k;
+                            row_lo = row0 + r;
+                        }
+                        if (changed >> 16) {
+                            col_hi = jj;
+                            int r = R - 1;
+#pragma unroll
+                            for (int k = R - 1; k >= 0; --k) if (((Hold[k] ^ best) >> 16) == 0) r = k;
+                            row_hi = row0 + r;
+                        }
+                        bestprev = best;
+                    }
+                }
+            }
+
+            // ---- tile epilogue: warp arg-best per half, merge into the running best (later tiles hold larger rows)
+            int s = (int)(best & 0xffffu) - bias, c = col_lo, r = row_lo;
+            if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
+            warp_argbest(s, c, r);
+            if (s > bs0 || (s == bs0 && s > 0 && c < bc0)) { bs0 = s; bc0 = c; br0 = r; }
+            s = (int)(best >> 16) - bias; c = col_hi; r = row_hi;
+            if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
+            warp_argbest(s, c, r);
+            if (s > bs1 || (s == bs1 && s > 0 && c < bc1)) { bs1 = s; bc1 = c; br1 = r; }
+        }
+
+        if (lane == 0) {
+            SwResult res;
+            res.score[0] = bs0; res.row[0] = br0; res.col[0] = bc0;
+            res.score[1] = bs1; res.row[1] = br1; res.col[1] = bc1;
+            p.results[task.out] = res;
+        }
+    }
+}
+
+}  // namespace nmsv

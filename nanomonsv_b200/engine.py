@@ -1,0 +1,247 @@
+"""Python face of the CUDA engine: packs sequences into the byte-coded batch layout and calls the C ABI.
+
+Nothing here computes alignments; every method ends in a call into libnmsv_sw.so and raises if that fails.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ALN_DTYPE, READ_DTYPE, RECORD_DTYPE, SSW_RESULT_DTYPE, SV_DTYPE, Scoring, Stats
+from .my_seq import CODE_LUT
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libnmsv_sw error {code}: {message}")
+        self.code = code
+
+
+DEFAULT_SCORING = (2, -2, 3, 1)   # matrix_create("ACGT", 2, -2); ssw(..., 3, 1, ...)  (count_sread_by_alignment.py:139,148)
+
+
+def _scoring(s) -> Scoring:
+    if isinstance(s, Scoring):
+        return s
+    match, mismatch, gap_open, gap_extend = s
+    return Scoring(int(match), int(mismatch), int(gap_open), int(gap_extend))
+
+
+class SeqPack:
+    """All sequences of one call in one uint8 code buffer: sequence i = codes[offsets[i] : offsets[i] + lens[i]]."""
+
+    def __init__(self, dedup: bool = False):
+        self._chunks: List[np.ndarray] = []
+        self._lens: List[int] = []
+        self._dedup = dedup
+        self._seen: Dict[str, int] = {}
+        self._frozen: Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]] = None
+
+    def add(self, seq: str) -> int:
+        """Add an ASCII sequence (encoded with the case-insensitive ACGT + wildcard mapper); returns its index."""
+        if self._dedup:
+            hit = self._seen.get(seq)
+            if hit is not None:
+                return hit
+        idx = self.add_codes(CODE_LUT[np.frombuffer(seq.encode("latin-1"), dtype=np.uint8)])
+        if self._dedup:
+            self._seen[seq] = idx
+        return idx
+
+    def add_codes(self, codes: np.ndarray) -> int:
+        assert self._frozen is None, "SeqPack already finalized"
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        self._chunks.append(codes)
+        self._lens.append(int(codes.shape[0]))
+        return len(self._lens) - 1
+
+    def __len__(self) -> int:
+        return len(self._lens)
+
+    def length(self, idx: int) -> int:
+        return self._lens[idx]
+
+    def finalize(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        if self._frozen is None:
+            lens = np.asarray(self._lens, dtype=np.uint32)
+            offsets = np.zeros(len(lens), dtype=np.uint64)
+            if len(lens) > 1:
+                np.cumsum(lens[:-1].astype(np.uint64), out=offsets[1:])
+            codes = np.concatenate(self._chunks) if self._chunks else np.zeros(0, dtype=np.uint8)
+            self._frozen = (np.ascontiguousarray(codes), offsets, lens)
+            self._chunks = []
+        return self._frozen
+
+    @staticmethod
+    def from_arrays(codes: np.ndarray, offsets: np.ndarray, lens: np.ndarray) -> "SeqPack":
+        p = SeqPack()
+        p._frozen = (np.ascontiguousarray(codes, dtype=np.uint8), np.ascontiguousarray(offsets, dtype=np.uint64),
+                     np.ascontiguousarray(lens, dtype=np.uint32))
+        p._lens = [int(x) for x in p._frozen[2]]
+        return p
+
+
+class Plan:
+    """A validation batch resident on the GPU (nmsv_plan_*): run() is the device-resident hot path."""
+
+    def __init__(self, engine: "Engine", handle: ctypes.c_void_p, n_svs: int, n_reads: int):
+        self._e, self._h, self.n_svs, self.n_reads = engine, handle, n_svs, n_reads
+
+    def run(self) -> None:
+        self._e._check(self._e._L.nmsv_plan_run(self._h))
+
+    def download(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        checked = np.zeros(self.n_svs, dtype=np.int32)
+        supporting = np.zeros(self.n_svs, dtype=np.int32)
+        records = np.zeros(max(self.n_reads, 1), dtype=RECORD_DTYPE)
+        n = ctypes.c_uint64(0)
+        self._e._check(self._e._L.nmsv_plan_download(self._h, checked.ctypes.data, supporting.ctypes.data,
+                                                     records.ctypes.data, len(records), ctypes.byref(n)))
+        records = records[:n.value]
+        return checked, supporting, records[np.argsort(records["read"], kind="stable")]
+
+    def download_alns(self) -> Tuple[np.ndarray, np.ndarray]:
+        alns = np.zeros((self.n_reads, 4), dtype=ALN_DTYPE)
+        flags = np.zeros(self.n_reads, dtype=np.uint8)
+        self._e._check(self._e._L.nmsv_plan_download_alns(self._h, alns.ctypes.data, flags.ctypes.data))
+        return alns, flags
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._e._check(self._e._L.nmsv_plan_stats(self._h, ctypes.byref(st)))
+        return st.asdict()
+
+    def close(self) -> None:
+        if self._h:
+            self._e._L.nmsv_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One CUDA context per process and GPU (mirrors one worker of --processes, reference run.py:361-372)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._L.nmsv_create(ctypes.byref(h), int(device))
+        if rc != 0:
+            raise EngineError(rc, (self._L.nmsv_last_error(None) or b"").decode())
+        self._h = h
+        self.device = int(device)
+
+    # ---- plumbing
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise EngineError(rc, (self._L.nmsv_last_error(self._h) or b"").decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.nmsv_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: Optional[int]) -> None:
+        """Launch on an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); None = own stream."""
+        self._check(self._L.nmsv_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr or 0)))
+
+    def device_info(self) -> dict:
+        sm, clk = ctypes.c_int32(), ctypes.c_int32()
+        l2, mem = ctypes.c_int64(), ctypes.c_int64()
+        name = ctypes.create_string_buffer(256)
+        self._check(self._L.nmsv_device_info(self._h, ctypes.byref(sm), ctypes.byref(clk), ctypes.byref(l2),
+                                             ctypes.byref(mem), name, 256))
+        return {"name": name.value.decode(), "sm_count": sm.value, "sm_clock_khz": clk.value,
+                "l2_bytes": l2.value, "global_mem_bytes": mem.value}
+
+    # ---- operator seam: parasail.ssw, batched
+    def ssw_batch(self, pack: SeqPack, tmpl_idx: Sequence[int], read_idx: Sequence[int],
+                  scoring=DEFAULT_SCORING, want_begin: bool = True) -> np.ndarray:
+        codes, offsets, lens = pack.finalize()
+        t = np.ascontiguousarray(tmpl_idx, dtype=np.uint32)
+        r = np.ascontiguousarray(read_idx, dtype=np.uint32)
+        assert t.shape == r.shape
+        out = np.zeros(len(t), dtype=SSW_RESULT_DTYPE)
+        sc = _scoring(scoring)
+        self._check(self._L.nmsv_ssw_batch(self._h, codes.ctypes.data, codes.size, offsets.ctypes.data,
+                                           lens.ctypes.data, len(lens), t.ctypes.data, r.ctypes.data, len(t),
+                                           ctypes.byref(sc), 1 if want_begin else 0, out.ctypes.data))
+        return out
+
+    # ---- function seam: ssw_check, batched (template + reverse complement, strand rule, 1-based)
+    def ssw_check_batch(self, pack: SeqPack, tmpl_idx: Sequence[int], read_idx: Sequence[int],
+                        tmpl_rc_idx: Optional[Sequence[int]] = None, scoring=DEFAULT_SCORING) -> np.ndarray:
+        codes, offsets, lens = pack.finalize()
+        t = np.ascontiguousarray(tmpl_idx, dtype=np.uint32)
+        r = np.ascontiguousarray(read_idx, dtype=np.uint32)
+        rc = None if tmpl_rc_idx is None else np.ascontiguousarray(tmpl_rc_idx, dtype=np.uint32)
+        out = np.zeros(len(t), dtype=ALN_DTYPE)
+        sc = _scoring(scoring)
+        self._check(self._L.nmsv_ssw_check_batch(self._h, codes.ctypes.data, codes.size, offsets.ctypes.data,
+                                                 lens.ctypes.data, len(lens), t.ctypes.data,
+                                                 None if rc is None else rc.ctypes.data, r.ctypes.data, len(t),
+                                                 ctypes.byref(sc), out.ctypes.data))
+        return out
+
+    # ---- stage seam
+    def plan(self, pack: SeqPack, svs: np.ndarray, reads: np.ndarray, scoring=DEFAULT_SCORING) -> Plan:
+        codes, offsets, lens = pack.finalize()
+        svs = np.ascontiguousarray(svs, dtype=SV_DTYPE)
+        reads = np.ascontiguousarray(reads, dtype=READ_DTYPE)
+        sc = _scoring(scoring)
+        h = ctypes.c_void_p()
+        self._check(self._L.nmsv_plan_create(self._h, ctypes.byref(h), codes.ctypes.data, codes.size,
+                                             offsets.ctypes.data, lens.ctypes.data, len(lens), svs.ctypes.data,
+                                             len(svs), reads.ctypes.data, len(reads), ctypes.byref(sc)))
+        return Plan(self, h, len(svs), len(reads))
+
+    def validate(self, pack: SeqPack, svs: np.ndarray, reads: np.ndarray,
+                 scoring=DEFAULT_SCORING) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """One-shot nmsv_validate_batch: host buffers in, (checked, supporting, records sorted by read) out."""
+        codes, offsets, lens = pack.finalize()
+        svs = np.ascontiguousarray(svs, dtype=SV_DTYPE)
+        reads = np.ascontiguousarray(reads, dtype=READ_DTYPE)
+        checked = np.zeros(len(svs), dtype=np.int32)
+        supporting = np.zeros(len(svs), dtype=np.int32)
+        records = np.zeros(max(len(reads), 1), dtype=RECORD_DTYPE)
+        n = ctypes.c_uint64(0)
+        sc = _scoring(scoring)
+        self._check(self._L.nmsv_validate_batch(self._h, codes.ctypes.data, codes.size, offsets.ctypes.data,
+                                                lens.ctypes.data, len(lens), svs.ctypes.data, len(svs),
+                                                reads.ctypes.data, len(reads), ctypes.byref(sc),
+                                                checked.ctypes.data, supporting.ctypes.data, records.ctypes.data,
+                                                len(records), ctypes.byref(n)))
+        records = records[:n.value]
+        return checked, supporting, records[np.argsort(records["read"], kind="stable")]
+
+
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    """Process-wide engine on the GPU selected by LOCAL_RANK (one process per GPU) or device 0."""
+    global _default_engine
+    if _default_engine is None:
+        import os
+        _default_engine = Engine(int(os.environ.get("NMSV_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+    return _default_engine

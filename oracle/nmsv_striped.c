@@ -9,6 +9,8 @@
  *   (1) an independent second formulation the scalar oracle (nmsv_oracle.c) is cross-checked against;
  *   (2) the timed host-CPU baseline of bench.py (cpu_baseline / --impl reference), multi-threaded with pthreads,
  *       one alignment per thread at a time (mirrors nanomonsv --processes sharding, reference run.py:324-379).
+ * Like Farrar's algorithm (and parasail's code) the lazy-F early exit is exact only for gap_open > gap_extend;
+ * the validation path always calls with open=3, extend=1 (count_sread_by_alignment.py:148).
  * It is NOT parasail and is reported as "parasail-equivalent (port)".  PARITY UNPINNED against real parasail.
  *
  * Reference call sites this stands in for: nanomonsv/count_sread_by_alignment.py:148-149.

@@ -1,0 +1,145 @@
+"""CPU tests: the C-ABI library builds, loads and exports what include/nmsv.h declares; host logic."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nanomonsv_b200
+from nanomonsv_b200 import _lib, batch, count_sread_by_alignment as C, my_seq, synth
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "nmsv.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nmsv_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    declared = _header_functions()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/nmsv.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert L.nmsv_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert _lib.SV_DTYPE.itemsize == 80
+    assert _lib.READ_DTYPE.itemsize == 16
+    assert _lib.ALN_DTYPE.itemsize == 24
+    assert _lib.RECORD_DTYPE.itemsize == 104
+    assert _lib.SSW_RESULT_DTYPE.itemsize == 20
+    assert ctypes.sizeof(_lib.Stats) == 72
+
+
+def test_encode_ascii_matches_python_lut():
+    L = _lib.load()
+    s = bytes(range(1, 256))
+    out = np.zeros(len(s), dtype=np.uint8)
+    L.nmsv_encode_ascii(s, len(s), out.ctypes.data)
+    assert (out == my_seq.CODE_LUT[np.frombuffer(s, dtype=np.uint8)]).all()
+    assert (out == O.encode(s.decode("latin-1"))).all()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(nanomonsv_b200.EngineError) as e:
+        nanomonsv_b200.Engine(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_integer_bounds_equal_float_comparisons():
+    for ratio in (1.2, 1.4, 1.6, 1.8):
+        for length in list(range(1, 700)) + [2000, 2001, 6000]:
+            smin, qmax, emin = batch.integer_bounds(length, ratio, 0.1, 0.9)
+            for score in (smin - 1, smin):
+                assert (score > ratio * length) == (score >= smin)
+            for q in (qmax, qmax + 1):
+                assert (q < 0.1 * length) == (q <= qmax)
+            for q in (emin - 1, emin):
+                assert (q > 0.9 * length) == (q >= emin)
+    assert batch.integer_bounds(401, 1.8, 0.1, 0.9)[0] == math.floor(721.8000000000001) + 1
+
+
+def test_reverse_complement_matches_oracle():
+    rng = np.random.default_rng(3)
+    alpha = "ACGTNacgtnWSMKRYBDHVxX-"
+    for _ in range(500):
+        s = "".join(alpha[i] for i in rng.integers(0, len(alpha), size=int(rng.integers(0, 50))))
+        assert my_seq.reverse_complement(s) == O.reverse_complement(s)
+    assert my_seq.needs_explicit_revcomp("ACGa") and not my_seq.needs_explicit_revcomp("ACGTN")
+
+
+def test_templates_match_oracle_restatement():
+    cfg = synth.SynthConfig(n_sv=40, contig_len=120000, n_contigs=3, read_len_max=3000, read_len_mean=1000,
+                            read_len_min=500, coverage=0.0, seed=5, short_fraction=0.5)
+    wl = synth.make_workload(cfg, samples=())
+    fasta = wl.fasta
+    n_short = 0
+    for sv in wl.svs:
+        for L in (200, 1000):
+            assert C.canonical_templates(sv.key, fasta, L) == O.sv_templates(sv.key, fasta, L)
+        n_short += C.canonical_templates(sv.key, fasta, 200)[4]
+    assert 0 < n_short < len(wl.svs)
+    # near a contig start the left flank is clipped (reference :239: max(pos - L - 1, 0))
+    key = "chr1,50,+,chr2,1000,-,---,r_0"
+    v1, v2, r1, r2, short = C.canonical_templates(key, fasta, 200)
+    assert (v1, v2, r1, r2, short) == O.sv_templates(key, fasta, 200)
+    assert len(r1) == 249 and len(v1) == 49 + 200
+    # the is_short_del_dup quirk: span + len(str(len(id))) < 300, insertion length ignored (:210-223)
+    assert C.canonical_templates("chr1,1000,+,chr1,1298,-,---,r_1", fasta, 200)[4] is True     # 298 + len("0") = 299
+    assert C.canonical_templates("chr1,1000,+,chr1,1299,-,---,r_1", fasta, 200)[4] is False
+    assert C.canonical_templates("chr1,1000,+,chr1,1298,-,ACGT,r_1", fasta, 200)[4] is True    # len(str(len("r_1"))) = 1
+    assert C.canonical_templates("chr1,1000,+,chr1,1298,-,ACGT,r_123456789", fasta, 200)[4] is False  # len("11") = 2
+    sb = synth.make_workload(synth.SynthConfig(n_sv=10, sbnd=True, contig_len=150000, n_contigs=2, read_len_max=3000,
+                                               coverage=0.0, seed=6, validate_sequence_length=200), samples=())
+    for sv in sb.svs:
+        var1, ref1 = C.sbnd_templates(sv.key, sb.fasta, 200)
+        assert (var1, ref1) == O.sbnd_templates(sv.key, sb.fasta, 200)
+        assert len(var1) in (601, 400) or len(sv.key.split(",")[3]) < 200
+
+
+def test_read_fasta_semantics(tmp_path):
+    p = tmp_path / "r.fa"
+    p.write_text(">a desc\nACGT\nAC\n>empty\n>b\nTT\n>last\n")
+    assert list(C.read_fasta(str(p))) == list(O.fasta_records(str(p))) == [("a", "ACGTAC"), ("b", "TT"), ("last", "")]
+
+
+def test_batch_builder_layout():
+    bb = batch.BatchBuilder(score_ratio_thres=1.2, var_read_min_mapq=40)
+    bb.add_sv(["ACGT" * 100, "ACGT" * 100, None, None], False, False)
+    bb.add_read("ACGT" * 300, 60, None)
+    bb.add_read(np.zeros(50, dtype=np.uint8), 3, 60)
+    bb.add_sv(["ACGa" * 50, None, "TTTT" * 50, None], True, False)
+    pack, svs, reads = bb.finalize()
+    codes, offsets, lens = pack.finalize()
+    assert svs["tmpl"][0][0] == svs["tmpl"][0][1] and svs["tmpl"][0][2] == _lib.NMSV_NONE
+    assert tuple(svs["score_min"][0]) == (481, 481) and tuple(svs["qstart_max"][0]) == (39, 39)
+    assert (svs["read_begin"][0], svs["read_end"][0]) == (0, 2) and (svs["read_begin"][1], svs["read_end"][1]) == (2, 2)
+    assert svs["tmpl_rc"][1][0] != _lib.NMSV_NONE and svs["flags"][1] == _lib.SV_SBND
+    assert reads["mapq2"][0] == _lib.MAPQ_NONE and reads["sv"].tolist() == [0, 0]
+    assert codes.size == int(lens.sum()) and offsets[-1] + lens[-1] == codes.size
+
+
+def test_synth_workload_is_deterministic_and_shaped():
+    cfg = synth.SynthConfig(n_sv=12, contig_len=150000, n_contigs=2, read_len_mean=2000, read_len_min=800,
+                            read_len_max=5000, coverage=10.0, seed=9, validate_sequence_length=200)
+    a, b = synth.make_workload(cfg), synth.make_workload(cfg)
+    assert [s.key for s in a.svs] == [s.key for s in b.svs]
+    for sample in ("tumor", "control"):
+        for ra, rb in zip(a.samples[sample], b.samples[sample]):
+            assert [r.rid for r in ra] == [r.rid for r in rb]
+            assert all((x.codes == y.codes).all() for x, y in zip(ra, rb))
+    n_t = sum(len(x) for x in a.samples["tumor"])
+    assert 12 * 10 <= n_t <= 12 * 30
+    pack, svs, reads = a.to_batch("tumor")
+    assert len(svs) == 12 and len(reads) == n_t
