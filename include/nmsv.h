@@ -141,9 +141,13 @@ int nmsv_abi_version(void);
 int nmsv_create(nmsv_ctx **ctx, int device);          /* one ctx per process/GPU (mirrors --processes, run.py:367) */
 void nmsv_destroy(nmsv_ctx *ctx);
 const char *nmsv_last_error(const nmsv_ctx *ctx);     /* ctx may be NULL: error of a failed nmsv_create */
-int nmsv_set_stream(nmsv_ctx *ctx, void *cuda_stream); /* cudaStream_t to launch on (NULL = ctx's own stream) */
+int nmsv_set_stream(nmsv_ctx *ctx, void *cuda_stream); /* cudaStream_t to launch on; NULL = the ctx's own non-blocking
+                                                          stream (pass cudaStreamLegacy to use the default stream) */
 int nmsv_device_info(const nmsv_ctx *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int64_t *l2_bytes,
                      int64_t *global_mem_bytes, char *name, size_t name_len);
+
+/* sustained VIADDMNMX.S16x2 issue rate of this GPU in lane-instructions/s (register-only loop): the integer roofline */
+int nmsv_measure_dpx_peak(nmsv_ctx *ctx, double *lane_inst_per_s);
 
 /* byte -> code with the mapper of parasail.matrix_create("ACGT", ...): case-insensitive ACGT, rest wildcard */
 void nmsv_encode_ascii(const char *ascii, uint64_t n, uint8_t *codes);
@@ -178,6 +182,14 @@ int nmsv_plan_run(nmsv_plan *plan);
 int nmsv_plan_download(nmsv_plan *plan, int32_t *checked, int32_t *supporting, nmsv_record *records,
                        uint64_t record_capacity, uint64_t *n_records);
 int nmsv_plan_stats(const nmsv_plan *plan, nmsv_stats *stats);
+/* measurement hooks: per-launch durations by CUDA events recorded on the launching stream (phase: 0 plan, 1 forward
+ * wavefront, 2 decide, 3 begin-pass wavefront, 4 final; rclass = strip height R of a wavefront launch) */
+int nmsv_plan_set_profiling(nmsv_plan *plan, int on);
+int nmsv_plan_kernel_times(nmsv_plan *plan, float *ms, uint32_t *phase, uint32_t *rclass, uint32_t capacity,
+                           uint32_t *n_launches);
+/* copy supporting[n_svs] (int32) of the last run into a caller-owned DEVICE buffer on the ctx stream, e.g. the
+ * send buffer of the NCCL gather that merges the per-GPU SV shards */
+int nmsv_plan_copy_counts_device(nmsv_plan *plan, void *d_supporting_int32);
 /* per (read, slot) alignment tuples of the last run, reads*4 entries; begin coordinates (qstart for '+',
  * qend for '-', tstart) are only filled for reads that reached the begin pass (debug / parity tests) */
 int nmsv_plan_download_alns(nmsv_plan *plan, nmsv_aln *alns, uint8_t *read_flags);

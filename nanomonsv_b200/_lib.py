@@ -50,7 +50,8 @@ class Stats(ctypes.Structure):
 EXPORTS = ["nmsv_abi_version", "nmsv_create", "nmsv_destroy", "nmsv_last_error", "nmsv_set_stream",
            "nmsv_device_info", "nmsv_encode_ascii", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
            "nmsv_plan_create", "nmsv_plan_run", "nmsv_plan_download", "nmsv_plan_stats", "nmsv_plan_download_alns",
-           "nmsv_plan_destroy"]
+           "nmsv_plan_destroy", "nmsv_plan_set_profiling", "nmsv_plan_kernel_times", "nmsv_plan_copy_counts_device",
+           "nmsv_measure_dpx_peak"]
 
 _lib = None
 
@@ -111,5 +112,13 @@ def load() -> ctypes.CDLL:
     L.nmsv_plan_download_alns.restype = ctypes.c_int
     L.nmsv_plan_destroy.argtypes = [vp]
     L.nmsv_plan_destroy.restype = None
+    L.nmsv_plan_set_profiling.argtypes = [vp, ctypes.c_int]
+    L.nmsv_plan_set_profiling.restype = ctypes.c_int
+    L.nmsv_plan_kernel_times.argtypes = [vp, vp, vp, vp, u32, ctypes.POINTER(u32)]
+    L.nmsv_plan_kernel_times.restype = ctypes.c_int
+    L.nmsv_plan_copy_counts_device.argtypes = [vp, vp]
+    L.nmsv_plan_copy_counts_device.restype = ctypes.c_int
+    L.nmsv_measure_dpx_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
+    L.nmsv_measure_dpx_peak.restype = ctypes.c_int
     _lib = L
     return L

@@ -214,6 +214,50 @@ extern "C" void nmsv_encode_ascii(const char* ascii, uint64_t n, uint8_t* codes)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// integer roofline: sustained DPX issue rate, measured on the device that runs the kernels
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dpx_peak_kernel(uint32_t* out, uint32_t seed, uint32_t k1, int iters)
+{
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = seed + threadIdx.x * 3u + i; b[i] = seed ^ (i * 77u); }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = __viaddmax_s16x2(a[i], k1, b[i]);
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r ^= a[i];
+    if (r == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+extern "C" int nmsv_measure_dpx_peak(nmsv_ctx* ctx, double* lane_inst_per_s)
+{
+    if (!ctx || !lane_inst_per_s) return NMSV_E_INVALID;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 8192;
+    uint32_t* d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&d, sizeof(uint32_t) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0));
+    CUDA_TRY(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0, ctx->stream);
+        dpx_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, 12345u, 0xfffdfffdu, iters);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    CUDA_TRY(ctx, cudaGetLastError());
+    *lane_inst_per_s = (double)blocks * threads * iters * 8.0 / (best * 1e-3);
+    return NMSV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // device buffers (stream-ordered pool)
 // ------------------------------------------------------------------------------------------------------------------
 struct DevBuf {
@@ -609,7 +653,25 @@ struct nmsv_plan {
     std::vector<int32_t> checked;
     nmsv_stats stats{};
     bool ran = false;
+    // per-launch CUDA-event timing (nmsv_plan_set_profiling): events are recorded on the launching stream
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    std::vector<uint32_t> launch_phase, launch_rclass;
+    ~nmsv_plan() { for (cudaEvent_t e : events) cudaEventDestroy(e); }
 };
+
+enum : uint32_t { kPhasePlan = 0, kPhaseFwd = 1, kPhaseDecide = 2, kPhaseRev = 3, kPhaseFinal = 4 };
+
+static void mark(nmsv_plan* pl, size_t& slot, cudaStream_t s)
+{
+    if (!pl->profiling) return;
+    if (slot >= pl->events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        pl->events.push_back(e);
+    }
+    cudaEventRecord(pl->events[slot++], s);
+}
 
 extern "C" void nmsv_plan_destroy(nmsv_plan* plan)
 {
@@ -756,10 +818,15 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     if (n_reads == 0) return NMSV_OK;
     const int tpb = 128;
     const uint32_t nslots = n_reads * 4u;
+    size_t ev = 0;
+    pl->launch_phase.clear(); pl->launch_rclass.clear();
+    auto note = [&](uint32_t phase, uint32_t rclass) { pl->launch_phase.push_back(phase); pl->launch_rclass.push_back(rclass); };
+    mark(pl, ev, s);
 
     plan_fwd_kernel<<<(nslots + tpb - 1) / tpb, tpb, 0, s>>>(pl->svs.as<nmsv_sv>(), pl->reads.as<nmsv_read>(),
         pl->order.as<uint32_t>(), pl->st.offsets.as<uint64_t>(), pl->st.lens.as<uint32_t>(), pl->st.seq_class.as<uint8_t>(),
         n_reads, pl->tasks.as<SwTask>());
+    note(kPhasePlan, 0); mark(pl, ev, s);
 
     SwParams sp;
     sp.codes = pl->st.codes.as<uint8_t>();
@@ -770,6 +837,7 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     for (size_t i = 0; i < pl->classes.size(); ++i) {
         sp.queue_head = pl->counters.as<uint32_t>() + kCntFwdQueue + i;
         launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
+        note(kPhaseFwd, (uint32_t)kClassR[pl->classes[i]]); mark(pl, ev, s);
     }
 
     DecideParams dp;
@@ -779,12 +847,14 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     dp.rev_tasks = pl->rev_tasks.as<SwTask>(); dp.counters = pl->counters.as<uint32_t>();
     dp.match = pl->sc.match; dp.open = pl->sc.gap_open; dp.ext = pl->sc.gap_extend;
     decide_kernel<<<(n_reads + tpb - 1) / tpb, tpb, 0, s>>>(dp);
+    note(kPhaseDecide, 0); mark(pl, ev, s);
 
     sp.tasks = pl->rev_tasks.as<SwTask>(); sp.n_tasks_dev = pl->counters.as<uint32_t>() + kCntRevTasks; sp.n_tasks = 0;
     sp.results = pl->rev.as<SwResult>();
     for (size_t i = 0; i < pl->classes.size(); ++i) {
         sp.queue_head = pl->counters.as<uint32_t>() + kCntRevQueue + i;
         launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
+        note(kPhaseRev, (uint32_t)kClassR[pl->classes[i]]); mark(pl, ev, s);
     }
 
     FinalParams fp;
@@ -793,7 +863,47 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     fp.supporting = pl->supporting.as<int32_t>(); fp.records = pl->records.as<nmsv_record>();
     fp.record_capacity = n_reads; fp.counters = dp.counters;
     final_kernel<<<(n_reads + tpb - 1) / tpb, tpb, 0, s>>>(fp);
+    note(kPhaseFinal, 0); mark(pl, ev, s);
     CUDA_TRY(ctx, cudaGetLastError());
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_plan_set_profiling(nmsv_plan* pl, int on)
+{
+    if (!pl) return NMSV_E_INVALID;
+    pl->profiling = on != 0;
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_plan_kernel_times(nmsv_plan* pl, float* ms, uint32_t* phase, uint32_t* rclass, uint32_t capacity,
+                                      uint32_t* n_launches)
+{
+    if (!pl || !n_launches) return NMSV_E_INVALID;
+    nmsv_ctx* ctx = pl->ctx;
+    const uint32_t n = (uint32_t)pl->launch_phase.size();
+    *n_launches = n;
+    if (!pl->profiling || !pl->ran || pl->events.size() < (size_t)n + 1)
+        return set_err(ctx, NMSV_E_INVALID, "nmsv_plan_kernel_times needs a run with profiling enabled");
+    if (capacity < n) return set_err(ctx, NMSV_E_CAPACITY, "kernel time buffers hold %u entries, %u launches", capacity, n);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaEventSynchronize(pl->events[n]));
+    for (uint32_t i = 0; i < n; ++i) {
+        if (ms) CUDA_TRY(ctx, cudaEventElapsedTime(&ms[i], pl->events[i], pl->events[i + 1]));
+        if (phase) phase[i] = pl->launch_phase[i];
+        if (rclass) rclass[i] = pl->launch_rclass[i];
+    }
+    return NMSV_OK;
+}
+
+extern "C" int nmsv_plan_copy_counts_device(nmsv_plan* pl, void* d_supporting_int32)
+{
+    if (!pl || !d_supporting_int32) return NMSV_E_INVALID;
+    nmsv_ctx* ctx = pl->ctx;
+    if (!pl->ran) return set_err(ctx, NMSV_E_INVALID, "nmsv_plan_copy_counts_device before nmsv_plan_run");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (pl->n_svs)
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_supporting_int32, pl->supporting.p, sizeof(int32_t) * pl->n_svs,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
     return NMSV_OK;
 }
 

@@ -110,6 +110,24 @@ class Plan:
         self._e._check(self._e._L.nmsv_plan_download_alns(self._h, alns.ctypes.data, flags.ctypes.data))
         return alns, flags
 
+    def set_profiling(self, on: bool = True) -> None:
+        self._e._check(self._e._L.nmsv_plan_set_profiling(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """[(phase, strip height R, milliseconds)] of the launches of the last run (CUDA events on the stream)."""
+        cap = 64
+        ms = np.zeros(cap, dtype=np.float32)
+        phase = np.zeros(cap, dtype=np.uint32)
+        rclass = np.zeros(cap, dtype=np.uint32)
+        n = ctypes.c_uint32(0)
+        self._e._check(self._e._L.nmsv_plan_kernel_times(self._h, ms.ctypes.data, phase.ctypes.data,
+                                                         rclass.ctypes.data, cap, ctypes.byref(n)))
+        names = ["plan", "sw_forward", "decide", "sw_begin", "final"]
+        return [(names[int(phase[i])], int(rclass[i]), float(ms[i])) for i in range(n.value)]
+
+    def copy_counts_to_device(self, device_ptr: int) -> None:
+        self._e._check(self._e._L.nmsv_plan_copy_counts_device(self._h, ctypes.c_void_p(device_ptr)))
+
     def stats(self) -> dict:
         st = Stats()
         self._e._check(self._e._L.nmsv_plan_stats(self._h, ctypes.byref(st)))
@@ -173,6 +191,12 @@ class Engine:
                                              ctypes.byref(mem), name, 256))
         return {"name": name.value.decode(), "sm_count": sm.value, "sm_clock_khz": clk.value,
                 "l2_bytes": l2.value, "global_mem_bytes": mem.value}
+
+    def measure_dpx_peak(self) -> float:
+        """Sustained DPX (VIADDMNMX.S16x2) lane-instructions per second of this GPU."""
+        v = ctypes.c_double(0.0)
+        self._check(self._L.nmsv_measure_dpx_peak(self._h, ctypes.byref(v)))
+        return v.value
 
     # ---- operator seam: parasail.ssw, batched
     def ssw_batch(self, pack: SeqPack, tmpl_idx: Sequence[int], read_idx: Sequence[int],
