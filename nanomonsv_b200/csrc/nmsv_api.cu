@@ -582,7 +582,7 @@ static int check_scoring(nmsv_ctx* ctx, const nmsv_scoring* sc)
     if (!sc) return set_err(ctx, NMSV_E_INVALID, "scoring is NULL");
     if (sc->match <= 0 || sc->mismatch > 0 || sc->gap_open < 0 || sc->gap_extend < 0)
         return set_err(ctx, NMSV_E_INVALID, "scoring must have match > 0, mismatch <= 0, gap_open >= 0, gap_extend >= 0");
-    if (sc->gap_open + sc->gap_extend > 4096 || -sc->mismatch > 4096 || sc->match > 4096)
+    if (sc->gap_open + sc->gap_extend > 64 || -sc->mismatch > 64 || sc->match > 64)
         return set_err(ctx, NMSV_E_RANGE, "scoring parameters too large for 16-bit lanes");
     return NMSV_OK;
 }
@@ -603,7 +603,9 @@ static int check_template(nmsv_ctx* ctx, uint32_t idx, const uint32_t* lens, uin
     if (idx >= n_seqs) return set_err(ctx, NMSV_E_INVALID, "%s index %u out of range (n_seqs %u)", what, idx, n_seqs);
     if (lens[idx] == 0) return set_err(ctx, NMSV_E_INVALID, "%s %u is empty", what, idx);
     // parasail: NULL when any H exceeds INT16_MAX - max(matrix) - 1 ; H <= match * rows
-    if ((uint64_t)sc->match * lens[idx] + (uint64_t)(sc->gap_open + sc->gap_extend) > 32767u - (uint32_t)sc->match - 1u)
+    // plus the kernel's bias head-room: a = open+ext and one chunk of per-step ext increments
+    if ((uint64_t)sc->match * lens[idx] + (uint64_t)(sc->gap_open + sc->gap_extend) +
+            (uint64_t)(kChunk + 2) * sc->gap_extend > 32767u - (uint32_t)sc->match - 1u)
         return set_err(ctx, NMSV_E_RANGE, "%s %u of length %u could score beyond the 16-bit range (parasail.ssw would return None)",
                        what, idx, lens[idx]);
     return NMSV_OK;

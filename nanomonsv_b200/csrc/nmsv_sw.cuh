@@ -14,18 +14,20 @@
 //     free) so the inner loop has no compares; the read is staged through a shared-memory ring.
 //   * templates longer than one tile run tile after tile; the H/F row between two tiles goes through a per-warp
 //     global scratch that stays L2 resident (8 B per column).
-//   * all values carry the bias a = open+ext so that E-ext and F-ext are plain 32-bit adds (no borrow between
-//     the halves): they issue on the FMA pipe (IMAD.IADD) while the 4.5 DPX instructions per packed cell pair
-//     (VIADDMNMX.S16x2 x3, VIMNMX3.S16x2 x1.5) own the ALU pipe.
+//   * all values carry the bias a + beta_t (a = open+ext, beta_t grows by ext per step): F-ext is a plain 32-bit
+//     add with no borrow between the halves (FMA pipe, IMAD), E-ext needs no instruction at all, and the zero
+//     floor of local alignment is a register. Per packed cell pair: 4.5 DPX instructions on the ALU pipe
+//     (VIADDMNMX.S16x2 x3, VIMNMX3.S16x2 x1.5) + 1 IMAD.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace nmsv {
 
-constexpr int kPadCode = 5;        // column / row code that can never start or extend an alignment
-constexpr int kRowPad = 6;         // row beyond the end of a template half
-constexpr int kNumCodes = 6;       // A C G T wildcard pad
+constexpr int kPadCode = 4;        // columns outside the read use the wildcard code: it scores 0, so it can neither
+                                   // start an alignment nor raise a maximum (updates need a strict increase)
+constexpr int kRowPad = 6;         // row beyond the end of a template half: scores kPadScore against everything
+constexpr int kNumCodes = 5;       // A C G T wildcard
 constexpr int kPadScore = -128;
 constexpr int kChunk = 128;        // columns staged per refill
 constexpr int kWarpsPerBlock = 4;
@@ -70,7 +72,8 @@ template <int R>
 __host__ __device__ constexpr size_t warp_smem_bytes()
 {
     return (size_t)kNumCodes * groups_of<R>() * 32 * 16   // profile, uint4 [code][group][lane]
-         + (size_t)kChunk * 8                               // boundary ring, uint2 per column
+         + (size_t)kChunk * 8                               // boundary ring (inputs of lane 0), uint2 per column
+         + (size_t)32 * 8                                   // boundary staging (outputs of lane 31), one group
          + (size_t)2 * kChunk;                              // read ring, 1 byte per column
 }
 
@@ -88,9 +91,18 @@ __device__ __forceinline__ int fetch_code(const uint8_t* __restrict__ codes, uin
 
 __device__ __forceinline__ int sub_score(int rc, int b, int match, int mismatch)
 {
-    if (rc == kRowPad || b == kPadCode) return kPadScore;
+    if (rc == kRowPad) return kPadScore;
     if (rc > 3 || b > 3) return 0;
     return rc == b ? match : mismatch;
+}
+
+// x + k*65537 as one IMAD (FMA pipe): adds k to both 16-bit halves when no borrow/carry crosses the halves.
+// Written as mad.lo so that ptxas keeps it off the ALU pipe, which the DPX instructions saturate.
+__device__ __forceinline__ uint32_t add_halves(uint32_t x, int k)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, 65537, %2;" : "=r"(r) : "r"((uint32_t)k), "r"(x));
+    return r;
 }
 
 // lexicographic "better": higher score, then smaller column, then smaller row
@@ -117,16 +129,23 @@ sw_wavefront_kernel(const SwParams p)
     uint8_t* wbase = smem_raw + (size_t)warp * warp_smem_bytes<R>();
     uint4* prof = reinterpret_cast<uint4*>(wbase);
     uint2* bring = reinterpret_cast<uint2*>(wbase + (size_t)kNumCodes * G * 32 * 16);
-    uint8_t* rring = reinterpret_cast<uint8_t*>(bring + kChunk);
+    uint2* bstage = bring + kChunk;
+    uint8_t* rring = reinterpret_cast<uint8_t*>(bstage + 32);
     const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + warp;
     uint2* const bnd0 = p.bnd + (size_t)gwarp * 2 * p.bnd_stride;
 
     const uint32_t n_tasks = p.n_tasks_dev ? *p.n_tasks_dev : p.n_tasks;
+    // Every stored H/E/F value is  true value + a + beta_t  with a = open + ext and beta_t = (t - tbase) * ext:
+    //   * a keeps E - ext and F - ext non-negative in the low half, so they are plain 32-bit adds (FMA pipe);
+    //   * beta grows by ext per step, which turns  E' = max(H - open, E - ext)  into  max(H + (ext - open), E):
+    //     the horizontal gap extension costs no instruction at all. beta is rebased at chunk boundaries.
     const int bias = p.open + p.ext;
-    const uint32_t FLOOR = pack16(bias, bias);
-    const uint32_t NEG_OPEN = pack16(-p.open, -p.open);
-    const uint32_t NEG_EXT_ADD = (uint32_t)(-(p.ext * 65537));   // plain 32-bit add; no borrow because lo >= ext
-    const uint32_t EF_INIT = pack16(bias - p.open, bias - p.open);  // E = F = -open
+    const uint32_t FLOOR0 = pack16(bias, bias);
+    const uint32_t EF0 = pack16(bias - p.open, bias - p.open);          // E = F = -open
+    const uint32_t NEG_OPEN = pack16(-p.open, -p.open);                 // DPX add operand:  H - open
+    const uint32_t EXT_M_OPEN = pack16(p.ext - p.open, p.ext - p.open); // DPX add operand:  H + ext - open
+    const int ext = p.ext;
+    const bool is_lane0 = (lane == 0);
 
     for (;;) {
         uint32_t ti = 0;
@@ -142,7 +161,9 @@ sw_wavefront_kernel(const SwParams p)
         const bool c_rev = task.flags & kCRev;
         const int rows = a_len > b_len ? a_len : b_len;
         const int ntiles = (rows + 32 * R - 1) / (32 * R);
-        const int total_steps = ncols + 31;
+        const int total_steps = (ncols + 31 + 1) & ~1;   // even: the step body is unrolled twice (a pad step is inert)
+        // steps the bias may run before the 16-bit lanes could overflow (host guarantees >= kChunk)
+        const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext : 0x7fffffff;
 
         // running best over tiles, per half: {score, col, row}
         int bs0 = 0, bc0 = 0, br0 = a_len - 1;
@@ -153,9 +174,10 @@ sw_wavefront_kernel(const SwParams p)
             uint2* const bnd_in = bnd0 + (size_t)((tile + 1) & 1) * p.bnd_stride;
             uint2* const bnd_out = bnd0 + (size_t)(tile & 1) * p.bnd_stride;
             const bool write_bnd = (tile + 1 < ntiles);
+            const bool stage_lane = write_bnd && lane == 31;
 
             __syncwarp();
-            // ---- profile of this tile: prof[code][group][lane].{x,y,z,w} = (S_A | S_B << 16) of row 4*group+w
+            // ---- profile of this tile: prof[code][group][lane].{x,y,z,w} = (S_A | S_B << 16) + ext of row 4*group+w
             {
                 uint32_t* pw = reinterpret_cast<uint32_t*>(prof);
                 for (int k = 0; k < 4 * G; ++k) {
@@ -164,7 +186,8 @@ sw_wavefront_kernel(const SwParams p)
                     const int cb = (k < R && row < b_len) ? fetch_code(p.codes, task.b_base, row, b_rev, b_comp) : kRowPad;
 #pragma unroll
                     for (int b = 0; b < kNumCodes; ++b) {
-                        const uint32_t w = pack16(sub_score(ca, b, p.match, p.mismatch), sub_score(cb, b, p.match, p.mismatch));
+                        const uint32_t w = pack16(sub_score(ca, b, p.match, p.mismatch) + p.ext,
+                                                  sub_score(cb, b, p.match, p.mismatch) + p.ext);
                         pw[(((b * G) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = w;
                     }
                 }
@@ -172,99 +195,148 @@ sw_wavefront_kernel(const SwParams p)
                 for (int u = 0; u < (2 * kChunk) / 32; ++u) rring[u * 32 + lane] = (uint8_t)kPadCode;
             }
 
-            uint32_t Hold[R], E[R];
+            // H of the previous column ping-pongs between HA and HB over a 2-step unrolled body, so that no
+            // register moves are needed to keep Hdiag alive while the new column is written.
+            uint32_t HA[R], HB[R], E[R];
 #pragma unroll
-            for (int k = 0; k < R; ++k) { Hold[k] = FLOOR; E[k] = EF_INIT; }
-            uint32_t best = FLOOR, bestprev = FLOOR;
-            int col_lo = 0, row_lo = 0, col_hi = 0, row_hi = 0;   // only meaningful once best rose above FLOOR
-            uint32_t h_last = FLOOR, f_out = EF_INIT, diag = FLOOR;
+            for (int k = 0; k < R; ++k) { HA[k] = FLOOR0; HB[k] = FLOOR0; E[k] = EF0; }
+            // later tiles start their running maximum at (best of the earlier tiles - 1), per half
+            uint32_t bestprev = FLOOR0 + pack16(bs0 > 0 ? bs0 - 1 : 0, bs1 > 0 ? bs1 - 1 : 0), fl = FLOOR0;
+            int col_lo = 0, row_lo = 0, col_hi = 0, row_hi = 0;   // only meaningful once best rose above the floor
+            uint32_t h_last = FLOOR0, f_out = EF0, diag = FLOOR0;
             int jj = -lane - 1;
+            int tbase = -1;          // beta_t = (t - tbase) * ext ; state "after step -1" carries beta = 0
+
+            auto step = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const int t) {
+                ++jj;   // jj == t - lane : the column this lane works on
+                fl = add_halves(fl, ext);
+                uint32_t hin = __shfl_up_sync(kFull, h_last, 1);
+                uint32_t fin = __shfl_up_sync(kFull, f_out, 1);
+                const uint2 bv = bring[t & (kChunk - 1)];
+                if (is_lane0) { hin = bv.x; fin = bv.y; }
+                hin = add_halves(hin, ext);     // produced one step ago: lift to this step's bias
+                fin = add_halves(fin, ext);
+                const uint32_t b = rring[jj & (2 * kChunk - 1)];
+                const uint4* pp = prof + b * (G * 32) + lane;
+
+                uint32_t S[4 * G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const uint4 v = pp[g * 32];
+                    S[4 * g + 0] = v.x; S[4 * g + 1] = v.y; S[4 * g + 2] = v.z; S[4 * g + 3] = v.w;
+                }
+                uint32_t F = fin;
+#pragma unroll
+                for (int k = 0; k < R; ++k) {
+                    const uint32_t x = __viaddmax_s16x2(k == 0 ? diag : Hs[k - 1], S[k], E[k]);  // max(Hdiag + S, E)
+                    const uint32_t h = __vimax3_s16x2(x, F, fl);                                 // H = max(x, F, 0)
+                    const uint32_t fd = add_halves(F, -ext);                                     // F - ext (FMA pipe)
+                    E[k] = __viaddmax_s16x2(h, EXT_M_OPEN, E[k]);                                // E' = max(H-open, E-ext)
+                    F = __viaddmax_s16x2(h, NEG_OPEN, fd);                                       // F' for the next row
+                    Hd[k] = h;
+                }
+                diag = hin;
+                const uint32_t bp = add_halves(bestprev, ext);
+                uint32_t best = bp;
+#pragma unroll
+                for (int k = 0; k + 1 < R; k += 2) best = __vimax3_s16x2(best, Hd[k], Hd[k + 1]);
+                if (R & 1) best = __vimax3_s16x2(best, Hd[R - 1], Hd[R - 1]);
+                h_last = Hd[R - 1];
+                f_out = F;
+                if (stage_lane) bstage[t & 31] = make_uint2(h_last, f_out);
+
+                if (best != bp) {
+                    // rare: this lane's running maximum rose in this column -> remember column and first row
+                    const uint32_t changed = best ^ bp;
+                    if (changed & 0xffffu) {
+                        col_lo = jj;
+                        int r = R - 1;
+#pragma unroll
+                        for (int k = R - 1; k >= 0; --k) if (((Hd[k] ^ best) & 0xffffu) == 0) r = k;
+                        row_lo = row0 + r;
+                    }
+                    if (changed >> 16) {
+                        col_hi = jj;
+                        int r = R - 1;
+#pragma unroll
+                        for (int k = R - 1; k >= 0; --k) if (((Hd[k] ^ best) >> 16) == 0) r = k;
+                        row_hi = row0 + r;
+                    }
+                }
+                bestprev = best;
+            };
 
             for (int t0 = 0; t0 < total_steps; t0 += kChunk) {
+                // ---- rebase the bias when the next chunk could leave the 16-bit budget (warp-uniform, rare)
+                if (t0 + kChunk - tbase > budget_steps) {
+                    const uint32_t d = (uint32_t)((t0 - 1 - tbase) * ext) * 65537u;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) { HA[k] -= d; E[k] -= d; }
+                    bestprev -= d; fl -= d; h_last -= d; f_out -= d; diag -= d;
+                    tbase = t0 - 1;
+                }
                 // ---- refill: columns [t0, t0+kChunk) of the read ring and of the boundary ring
                 __syncwarp();
 #pragma unroll
                 for (int u = 0; u < kChunk / 32; ++u) {
                     const int col = t0 + u * 32 + lane;
                     uint8_t c = (uint8_t)kPadCode;
-                    uint2 bv = make_uint2(FLOOR, EF_INIT);
+                    uint2 bv = make_uint2(FLOOR0, EF0);
                     if (col < ncols) {
                         c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
                         if (tile > 0) bv = __ldcg(bnd_in + col);
                     }
+                    // lane 0 consumes entry `col` at step col and then adds ext: store with beta_{col-1}
+                    const uint32_t bb = (uint32_t)((col - 1 - tbase) * ext) * 65537u;
+                    bv.x += bb; bv.y += bb;
                     rring[col & (2 * kChunk - 1)] = c;
                     bring[col & (kChunk - 1)] = bv;
                 }
                 __syncwarp();
 
                 const int t1 = (t0 + kChunk < total_steps) ? t0 + kChunk : total_steps;
-                for (int t = t0; t < t1; ++t) {
-                    ++jj;   // jj == t - lane : the column this lane works on
-                    uint32_t hin = __shfl_up_sync(kFull, h_last, 1);
-                    uint32_t fin = __shfl_up_sync(kFull, f_out, 1);
-                    const uint2 bv = bring[t & (kChunk - 1)];
-                    if (lane == 0) { hin = bv.x; fin = bv.y; }
-                    const uint32_t b = rring[jj & (2 * kChunk - 1)];
-                    const uint4* pp = prof + b * (G * 32) + lane;
-
-                    uint32_t S[4 * G];
-#pragma unroll
-                    for (int g = 0; g < G; ++g) {
-                        const uint4 v = pp[g * 32];
-                        S[4 * g + 0] = v.x; S[4 * g + 1] = v.y; S[4 * g + 2] = v.z; S[4 * g + 3] = v.w;
+                for (int g0 = t0; g0 < t1; g0 += 32) {
+                    const int g1 = (g0 + 32 < t1) ? g0 + 32 : t1;     // g1 - g0 is even (total_steps is even)
+                    for (int t = g0; t < g1; t += 2) {
+                        step(HA, HB, t);
+                        step(HB, HA, t + 1);
                     }
-
-                    uint32_t hd = diag;
-                    diag = hin;
-                    uint32_t F = fin;
+                    // ---- event filter: only a cell that reaches the final maximum of the whole alignment matters, and
+                    //      any H seen so far is a lower bound of it. Lift every lane's running maximum to (warp-wide
+                    //      maximum - 1): lanes then take the slow path only for values that can still win or tie.
+                    {
+                        uint32_t wb = bestprev;
 #pragma unroll
-                    for (int k = 0; k < R; ++k) {
-                        const uint32_t x = __viaddmax_s16x2(hd, S[k], E[k]);        // max(Hdiag + S, E)
-                        const uint32_t h = __vimax3_s16x2(x, F, FLOOR);             // H = max(., F, 0)
-                        const uint32_t ed = E[k] + NEG_EXT_ADD;                     // E - ext   (FMA pipe)
-                        const uint32_t fd = F + NEG_EXT_ADD;                        // F - ext   (FMA pipe)
-                        E[k] = __viaddmax_s16x2(h, NEG_OPEN, ed);                   // E' = max(H - open, E - ext)
-                        F = __viaddmax_s16x2(h, NEG_OPEN, fd);                      // F' for the next row
-                        hd = Hold[k];
-                        Hold[k] = h;
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            const uint32_t o = __shfl_xor_sync(kFull, wb, off);
+                            wb = __vimax3_s16x2(wb, o, o);
+                        }
+                        const uint32_t lift = wb - 0x00010001u;      // both halves >= bias >= 1: no borrow
+                        bestprev = __vimax3_s16x2(bestprev, lift, lift);
                     }
-#pragma unroll
-                    for (int k = 0; k + 1 < R; k += 2) best = __vimax3_s16x2(best, Hold[k], Hold[k + 1]);
-                    if (R & 1) best = __vimax3_s16x2(best, Hold[R - 1], Hold[R - 1]);
-                    h_last = Hold[R - 1];
-                    f_out = F;
-
-                    if (write_bnd && lane == 31 && (unsigned)jj < (unsigned)ncols)
-                        __stcg(bnd_out + jj, make_uint2(h_last, f_out));
-
-                    if (best != bestprev) {
-                        // rare: this lane's running maximum rose in this column -> remember column and first row
-                        const uint32_t changed = best ^ bestprev;
-                        if (changed & 0xffffu) {
-                            col_lo = jj;
-                            int r = R - 1;
-#pragma unroll
-                            for (int k = R - 1; k >= 0; --k) if (((Hold[k] ^ best) & 0xffffu) == 0) r = k;
-                            row_lo = row0 + r;
+                    // ---- flush the staged boundary row of this group: entry q was produced at step g0+q for column
+                    //      g0+q-31; remove its bias and store 32 columns with one coalesced 256-byte write
+                    if (write_bnd) {
+                        __syncwarp();
+                        const int tp = g0 + lane;
+                        const int col = tp - 31;
+                        if (tp < g1 && col >= 0 && col < ncols) {
+                            uint2 v = bstage[lane];
+                            const uint32_t bb = (uint32_t)((tp - tbase) * ext) * 65537u;
+                            v.x -= bb; v.y -= bb;
+                            __stcg(bnd_out + col, v);
                         }
-                        if (changed >> 16) {
-                            col_hi = jj;
-                            int r = R - 1;
-#pragma unroll
-                            for (int k = R - 1; k >= 0; --k) if (((Hold[k] ^ best) >> 16) == 0) r = k;
-                            row_hi = row0 + r;
-                        }
-                        bestprev = best;
+                        __syncwarp();
                     }
                 }
             }
 
             // ---- tile epilogue: warp arg-best per half, merge into the running best (later tiles hold larger rows)
-            int s = (int)(best & 0xffffu) - bias, c = col_lo, r = row_lo;
+            int s = (int)(bestprev & 0xffffu) - (int)(fl & 0xffffu), c = col_lo, r = row_lo;
             if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
             warp_argbest(s, c, r);
             if (s > bs0 || (s == bs0 && s > 0 && c < bc0)) { bs0 = s; bc0 = c; br0 = r; }
-            s = (int)(best >> 16) - bias; c = col_hi; r = row_hi;
+            s = (int)(bestprev >> 16) - (int)(fl >> 16); c = col_hi; r = row_hi;
             if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
             warp_argbest(s, c, r);
             if (s > bs1 || (s == bs1 && s > 0 && c < bc1)) { bs1 = s; bc1 = c; br1 = r; }
