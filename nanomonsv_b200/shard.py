@@ -76,3 +76,18 @@ def gather_records(local_lines: List[str], group=None) -> List[str]:
     out: List[Optional[List[str]]] = [None] * dist.get_world_size(group)
     dist.all_gather_object(out, list(local_lines), group=group)
     return [ln for part in out for ln in (part or [])]
+
+
+def validate_sharded(costs: Sequence[float], run_local, rank: int, world: int, group=None, device=None,
+                     partition: str = "lpt"):
+    """Partition n = len(costs) SV candidates over `world` ranks, run `run_local(indices)` on this rank's share
+    (-> (checked[int], supporting[int], info_lines[str]) for those indices, in order) and merge: returns the dense
+    (n, 2) count table and all info lines, identical on every rank. `run_local` is the GPU path in production
+    (Alignment_counter on this rank's engine); the collective is the only communication."""
+    n = len(costs)
+    parts = lpt_partition(costs, world) if partition == "lpt" else round_robin_partition(n, world)
+    mine = parts[rank]
+    checked, supporting, lines = run_local(mine) if mine else ([], [], [])
+    table = merge_counts(n, mine, np.asarray(checked, dtype=np.int32), np.asarray(supporting, dtype=np.int32),
+                         group=group, device=device)
+    return table, gather_records(list(lines), group=group), parts
