@@ -41,6 +41,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout. Native libraries (NCCL's version banner, ...) write to fd 1 directly, so
+# fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------------
@@ -180,7 +190,7 @@ def reference_arm(args, rank: int):
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -353,7 +363,7 @@ def main():
                 "sample": f"{n_used} SV candidates of the same batch (tumor reads), {len(t)} alignments with "
                           f"reversed begin pass, {cells / 1e9:.1f} G forward cells in {dt:.1f}s; engine oracle/nmsv_striped.c "
                           f"(AVX2 striped, 8-bit then 16-bit: parasail-equivalent port, parasail not installable)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     plan.close()
     if world > 1:
         dist.destroy_process_group()

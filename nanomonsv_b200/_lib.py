@@ -65,8 +65,8 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.is_stale():
+    path = os.environ.get("NMSV_LIB_PATH") or _build.LIB_PATH      # NMSV_LIB_PATH: experiment builds only
+    if path == _build.LIB_PATH and _build.is_stale():
         try:
             _build.build()
         except Exception as exc:  # no silent fallback: say what is missing

@@ -25,7 +25,11 @@ using namespace nmsv;
 // ------------------------------------------------------------------------------------------------------------------
 // strip classes
 // ------------------------------------------------------------------------------------------------------------------
+#ifdef NMSV_EXP_R32
+static const int kClassR[] = {4, 8, 13, 16, 19, 32};
+#else
 static const int kClassR[] = {4, 8, 13, 16, 19};
+#endif
 static const int kNumClasses = (int)(sizeof(kClassR) / sizeof(kClassR[0]));
 
 static int choose_class(uint32_t len)
@@ -85,9 +89,16 @@ template <int R>
 static cudaError_t setup_class(int* blocks_per_sm)
 {
     const size_t smem = kWarpsPerBlock * warp_smem_bytes<R>();
-    cudaError_t e = cudaFuncSetAttribute(sw_wavefront_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sw_wavefront_kernel<R, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sw_wavefront_kernel<R>, kWarpsPerBlock * 32, smem);
+    e = cudaFuncSetAttribute(sw_wavefront_kernel<R, -1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int a = 0, b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sw_wavefront_kernel<R, 3, 1>, kWarpsPerBlock * 32, smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sw_wavefront_kernel<R, -1, -1>, kWarpsPerBlock * 32, smem);
+    *blocks_per_sm = a < b ? a : b;      // one grid size (and boundary scratch size) per class
+    return e;
 }
 
 static cudaError_t setup_class_idx(int cls, int* bps)
@@ -98,6 +109,9 @@ static cudaError_t setup_class_idx(int cls, int* bps)
     case 13: return setup_class<13>(bps);
     case 16: return setup_class<16>(bps);
     case 19: return setup_class<19>(bps);
+#ifdef NMSV_EXP_R32
+    case 32: return setup_class<32>(bps);
+#endif
     }
     return cudaErrorInvalidValue;
 }
@@ -105,7 +119,11 @@ static cudaError_t setup_class_idx(int cls, int* bps)
 template <int R>
 static void launch_class(const SwParams& p, int grid, cudaStream_t s)
 {
-    sw_wavefront_kernel<R><<<grid, kWarpsPerBlock * 32, kWarpsPerBlock * warp_smem_bytes<R>(), s>>>(p);
+    const size_t smem = kWarpsPerBlock * warp_smem_bytes<R>();
+    if (p.open == 3 && p.ext == 1)      // the reference's gap penalties: instantiation with immediate operands
+        sw_wavefront_kernel<R, 3, 1><<<grid, kWarpsPerBlock * 32, smem, s>>>(p);
+    else
+        sw_wavefront_kernel<R, -1, -1><<<grid, kWarpsPerBlock * 32, smem, s>>>(p);
 }
 
 static void launch_class_idx(int cls, const SwParams& p, int grid, cudaStream_t s)
@@ -116,7 +134,18 @@ static void launch_class_idx(int cls, const SwParams& p, int grid, cudaStream_t 
     case 13: launch_class<13>(p, grid, s); break;
     case 16: launch_class<16>(p, grid, s); break;
     case 19: launch_class<19>(p, grid, s); break;
+#ifdef NMSV_EXP_R32
+    case 32: launch_class<32>(p, grid, s); break;
+#endif
     }
+}
+
+static void fill_packed(SwParams& sp)
+{
+    auto pack = [](int v) { return ((uint32_t)(v & 0xffff) << 16) | (uint32_t)(v & 0xffff); };
+    sp.neg_open2 = pack(-sp.open);
+    sp.ext_m_open2 = pack(sp.ext - sp.open);
+    sp.ext2 = (uint32_t)sp.ext * 65537u;
 }
 
 extern "C" int nmsv_abi_version(void) { return NMSV_ABI_VERSION; }
@@ -834,6 +863,7 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     sp.codes = pl->st.codes.as<uint8_t>();
     sp.bnd = pl->bnd.as<uint2>(); sp.bnd_stride = pl->bnd_stride;
     sp.match = pl->sc.match; sp.mismatch = pl->sc.mismatch; sp.open = pl->sc.gap_open; sp.ext = pl->sc.gap_extend;
+    fill_packed(sp);
 
     sp.tasks = pl->tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = nslots; sp.results = pl->fwd.as<SwResult>();
     for (size_t i = 0; i < pl->classes.size(); ++i) {
@@ -1059,6 +1089,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     SwParams sp;
     sp.codes = st.codes.as<uint8_t>(); sp.bnd = bnd.as<uint2>(); sp.bnd_stride = stride;
     sp.match = sc->match; sp.mismatch = sc->mismatch; sp.open = sc->gap_open; sp.ext = sc->gap_extend;
+    fill_packed(sp);
     sp.tasks = tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = n_pairs; sp.results = fwd.as<SwResult>();
     for (size_t i = 0; i < classes.size(); ++i) {
         sp.queue_head = counters.as<uint32_t>() + kCntFwdQueue + i;

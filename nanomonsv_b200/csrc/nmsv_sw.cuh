@@ -30,7 +30,13 @@ constexpr int kRowPad = 6;         // row beyond the end of a template half: sco
 constexpr int kNumCodes = 5;       // A C G T wildcard
 constexpr int kPadScore = -128;
 constexpr int kChunk = 128;        // columns staged per refill
-constexpr int kWarpsPerBlock = 4;
+#ifndef NMSV_WPB
+#define NMSV_WPB 4
+#endif
+constexpr int kWarpsPerBlock = NMSV_WPB;   // independent warps per block (each owns its slice of shared memory)
+#ifndef NMSV_WARPS_PER_SM
+#define NMSV_WARPS_PER_SM 16
+#endif
 constexpr unsigned kFull = 0xffffffffu;
 
 enum : uint32_t { kARev = 1u, kAComp = 2u, kBRev = 4u, kBComp = 8u, kCRev = 16u };
@@ -63,6 +69,9 @@ struct SwParams {
     uint2* bnd;                    // [grid warps][2][bnd_stride] tile-boundary scratch
     uint32_t bnd_stride;
     int match, mismatch, open, ext;
+    uint32_t neg_open2;     // (-open, -open) packed: DPX add operand, read from the constant bank
+    uint32_t ext_m_open2;   // (ext-open, ext-open) packed
+    uint32_t ext2;          // ext * 65537
 };
 
 template <int R>
@@ -74,7 +83,8 @@ __host__ __device__ constexpr size_t warp_smem_bytes()
     return (size_t)kNumCodes * groups_of<R>() * 32 * 16   // profile, uint4 [code][group][lane]
          + (size_t)kChunk * 8                               // boundary ring (inputs of lane 0), uint2 per column
          + (size_t)32 * 8                                   // boundary staging (outputs of lane 31), one group
-         + (size_t)2 * kChunk;                              // read ring, 1 byte per column
+         + (size_t)16                                       // constant slot read by lanes 1..31 instead of the ring
+         + (size_t)4 * kChunk;                              // read ring, 1 byte per column, stored twice (mirrored)
 }
 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi)
@@ -118,8 +128,11 @@ __device__ __forceinline__ void warp_argbest(int& s, int& c, int& r)
     }
 }
 
-template <int R>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (R <= 16 ? 4 : 3))
+// OPEN/EXT >= 0: gap penalties known at compile time (the reference always calls parasail.ssw(.., 3, 1, ..),
+// count_sread_by_alignment.py:148): the DPX add operands become immediates, which saves one vector-register read on
+// two of the 4.5 DPX instructions per cell pair. OPEN = EXT = -1: generic instantiation, operands from the parameters.
+template <int R, int OPEN, int EXT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, ((R <= 16 ? NMSV_WARPS_PER_SM : (R <= 19 ? 12 : 8)) / kWarpsPerBlock > 0 ? (R <= 16 ? NMSV_WARPS_PER_SM : (R <= 19 ? 12 : 8)) / kWarpsPerBlock : 1))
 sw_wavefront_kernel(const SwParams p)
 {
     constexpr int G = groups_of<R>();
@@ -130,7 +143,8 @@ sw_wavefront_kernel(const SwParams p)
     uint4* prof = reinterpret_cast<uint4*>(wbase);
     uint2* bring = reinterpret_cast<uint2*>(wbase + (size_t)kNumCodes * G * 32 * 16);
     uint2* bstage = bring + kChunk;
-    uint8_t* rring = reinterpret_cast<uint8_t*>(bstage + 32);
+    uint2* bconst = bstage + 32;
+    uint8_t* rring = reinterpret_cast<uint8_t*>(bconst + 2);
     const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + warp;
     uint2* const bnd0 = p.bnd + (size_t)gwarp * 2 * p.bnd_stride;
 
@@ -142,10 +156,19 @@ sw_wavefront_kernel(const SwParams p)
     const int bias = p.open + p.ext;
     const uint32_t FLOOR0 = pack16(bias, bias);
     const uint32_t EF0 = pack16(bias - p.open, bias - p.open);          // E = F = -open
-    const uint32_t NEG_OPEN = pack16(-p.open, -p.open);                 // DPX add operand:  H - open
-    const uint32_t EXT_M_OPEN = pack16(p.ext - p.open, p.ext - p.open); // DPX add operand:  H + ext - open
+    constexpr bool kFixedGaps = (OPEN >= 0 && EXT >= 0);
+    const uint32_t NEG_OPEN = kFixedGaps ? (((uint32_t)(-OPEN) & 0xffffu) * 65537u) : p.neg_open2;            // H - open
+    const uint32_t EXT_M_OPEN = kFixedGaps ? (((uint32_t)(EXT - OPEN) & 0xffffu) * 65537u) : p.ext_m_open2;   // H + ext - open
     const int ext = p.ext;
     const bool is_lane0 = (lane == 0);
+    // lane 0 takes H/F of the row above its strip from the boundary ring, lanes 1..31 from lane-1 by shuffle. Instead
+    // of two SELs (ALU pipe) per step every lane does  in = shfl * m1 + ld  (IMAD): lane 0 has m1 = 0 and loads the
+    // ring entry of this step, the others have m1 = 1 and load a constant slot holding +ext (the bias lift).
+    const uint32_t m1 = is_lane0 ? 0u : 1u;
+    const char* const bsrc = is_lane0 ? reinterpret_cast<const char*>(bring) : reinterpret_cast<const char*>(bconst);
+    const uint32_t bstride = is_lane0 ? 8u : 0u;
+    // read ring: column j lives at rring[j & 255] and rring[(j & 255) + 256]; lane l reads (t & 255) + 256 - l
+    const uint8_t* const rlane = rring + 2 * kChunk - lane;
 
     for (;;) {
         uint32_t ti = 0;
@@ -192,7 +215,8 @@ sw_wavefront_kernel(const SwParams p)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < (2 * kChunk) / 32; ++u) rring[u * 32 + lane] = (uint8_t)kPadCode;
+                for (int u = 0; u < (4 * kChunk) / 32; ++u) rring[u * 32 + lane] = (uint8_t)kPadCode;
+                if (lane == 0) bconst[0] = make_uint2((uint32_t)(ext * 65537), (uint32_t)(ext * 65537));
             }
 
             // H of the previous column ping-pongs between HA and HB over a 2-step unrolled body, so that no
@@ -201,67 +225,77 @@ sw_wavefront_kernel(const SwParams p)
 #pragma unroll
             for (int k = 0; k < R; ++k) { HA[k] = FLOOR0; HB[k] = FLOOR0; E[k] = EF0; }
             // later tiles start their running maximum at (best of the earlier tiles - 1), per half
-            uint32_t bestprev = FLOOR0 + pack16(bs0 > 0 ? bs0 - 1 : 0, bs1 > 0 ? bs1 - 1 : 0), fl = FLOOR0;
+            uint32_t bestprev = FLOOR0 + pack16(bs0 > 0 ? bs0 - 1 : 0, bs1 > 0 ? bs1 - 1 : 0);
+            uint32_t flb = FLOOR0 + p.ext2;     // floor of step t is flb + t*ext2 = FLOOR0 + (t - tbase)*ext2, tbase = -1
             int col_lo = 0, row_lo = 0, col_hi = 0, row_hi = 0;   // only meaningful once best rose above the floor
             uint32_t h_last = FLOOR0, f_out = EF0, diag = FLOOR0;
-            int jj = -lane - 1;
             int tbase = -1;          // beta_t = (t - tbase) * ext ; state "after step -1" carries beta = 0
 
+            const uint32_t MARGIN = (uint32_t)((p.open + 2 * ext) * 65537);   // open + 2*ext in both halves
             auto step = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const int t) {
-                ++jj;   // jj == t - lane : the column this lane works on
-                fl = add_halves(fl, ext);
-                uint32_t hin = __shfl_up_sync(kFull, h_last, 1);
-                uint32_t fin = __shfl_up_sync(kFull, f_out, 1);
-                const uint2 bv = bring[t & (kChunk - 1)];
-                if (is_lane0) { hin = bv.x; fin = bv.y; }
-                hin = add_halves(hin, ext);     // produced one step ago: lift to this step's bias
-                fin = add_halves(fin, ext);
-                const uint32_t b = rring[jj & (2 * kChunk - 1)];
+                const uint32_t fl = flb + (uint32_t)t * p.ext2;    // floor of this step: warp-uniform
+#ifdef NMSV_EXP_NO_SHFL
+                const uint32_t sh = h_last, sf = f_out;
+#else
+                const uint32_t sh = __shfl_up_sync(kFull, h_last, 1);
+                const uint32_t sf = __shfl_up_sync(kFull, f_out, 1);
+#endif
+                const uint2 bv = *reinterpret_cast<const uint2*>(bsrc + (uint32_t)(t & (kChunk - 1)) * bstride);
+                uint32_t hin, fin;     // H / F of the row above this strip, lifted to this step's bias
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hin) : "r"(sh), "r"(m1), "r"(bv.x));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(fin) : "r"(sf), "r"(m1), "r"(bv.y));
+                const uint32_t b = rlane[t & (2 * kChunk - 1)];
                 const uint4* pp = prof + b * (G * 32) + lane;
 
                 uint32_t S[4 * G];
+#ifdef NMSV_EXP_NO_LDS
+#pragma unroll
+                for (int g = 0; g < 4 * G; ++g) S[g] = (uint32_t)(size_t)pp + g;
+#else
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const uint4 v = pp[g * 32];
                     S[4 * g + 0] = v.x; S[4 * g + 1] = v.y; S[4 * g + 2] = v.z; S[4 * g + 3] = v.w;
                 }
+#endif
                 uint32_t F = fin;
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     const uint32_t x = __viaddmax_s16x2(k == 0 ? diag : Hs[k - 1], S[k], E[k]);  // max(Hdiag + S, E)
-                    const uint32_t h = __vimax3_s16x2(x, F, fl);                                 // H = max(x, F, 0)
+                    const uint32_t h = __vimax3_s16x2(x, fl, F);                                 // H = max(x, F, 0)
                     const uint32_t fd = add_halves(F, -ext);                                     // F - ext (FMA pipe)
                     E[k] = __viaddmax_s16x2(h, EXT_M_OPEN, E[k]);                                // E' = max(H-open, E-ext)
                     F = __viaddmax_s16x2(h, NEG_OPEN, fd);                                       // F' for the next row
                     Hd[k] = h;
                 }
                 diag = hin;
-                const uint32_t bp = add_halves(bestprev, ext);
-                uint32_t best = bp;
-#pragma unroll
-                for (int k = 0; k + 1 < R; k += 2) best = __vimax3_s16x2(best, Hd[k], Hd[k + 1]);
-                if (R & 1) best = __vimax3_s16x2(best, Hd[R - 1], Hd[R - 1]);
                 h_last = Hd[R - 1];
                 f_out = F;
                 if (stage_lane) bstage[t & 31] = make_uint2(h_last, f_out);
 
-                if (best != bp) {
-                    // rare: this lane's running maximum rose in this column -> remember column and first row
-                    const uint32_t changed = best ^ bp;
-                    if (changed & 0xffffu) {
-                        col_lo = jj;
-                        int r = R - 1;
+                // ---- running maximum. Rows k and k' <= k of one column satisfy H[k] >= H[k'] - open - (k-k'-1)*ext
+                // (through F), so if no row of {R-1, R-5, ...} comes within open + 2*ext of the running maximum,
+                // no row of the strip exceeds it: 1 DPX per 8 rows instead of 1 per 2 rows in the common case.
+                const uint32_t bp = add_halves(bestprev, ext);
+                const uint32_t bpm = bp - MARGIN;                    // fl >= open + 2*ext: no borrow
+                uint32_t q = bpm;
 #pragma unroll
-                        for (int k = R - 1; k >= 0; --k) if (((Hd[k] ^ best) & 0xffffu) == 0) r = k;
-                        row_lo = row0 + r;
-                    }
-                    if (changed >> 16) {
-                        col_hi = jj;
-                        int r = R - 1;
+                for (int k = R - 1; k >= 0; k -= 8) q = __vimax3_s16x2(q, Hd[k], Hd[k >= 4 ? k - 4 : k]);
+                uint32_t best = bp;
+                if (q != bpm) {
+                    // rare: some row may exceed this lane's running maximum. One prefix-maximum pass: VIMNMX with
+                    // predicate outputs tells per half whether H[k] strictly beats everything before it; the last
+                    // such row is the first row holding the column maximum (parasail: smallest row).
+                    int rl = -1, rh = -1;
 #pragma unroll
-                        for (int k = R - 1; k >= 0; --k) if (((Hd[k] ^ best) >> 16) == 0) r = k;
-                        row_hi = row0 + r;
+                    for (int k = 0; k < R; ++k) {
+                        bool keep_hi, keep_lo;                       // keep_* = (best >= H[k]) in that half
+                        best = __vibmax_s16x2(best, Hd[k], &keep_hi, &keep_lo);
+                        if (!keep_lo) rl = k;
+                        if (!keep_hi) rh = k;
                     }
+                    if (rl >= 0) { col_lo = t - lane; row_lo = row0 + rl; }
+                    if (rh >= 0) { col_hi = t - lane; row_hi = row0 + rh; }
                 }
                 bestprev = best;
             };
@@ -272,8 +306,9 @@ sw_wavefront_kernel(const SwParams p)
                     const uint32_t d = (uint32_t)((t0 - 1 - tbase) * ext) * 65537u;
 #pragma unroll
                     for (int k = 0; k < R; ++k) { HA[k] -= d; E[k] -= d; }
-                    bestprev -= d; fl -= d; h_last -= d; f_out -= d; diag -= d;
+                    bestprev -= d; h_last -= d; f_out -= d; diag -= d;
                     tbase = t0 - 1;
+                    flb = FLOOR0 - (uint32_t)tbase * p.ext2;
                 }
                 // ---- refill: columns [t0, t0+kChunk) of the read ring and of the boundary ring
                 __syncwarp();
@@ -286,10 +321,11 @@ sw_wavefront_kernel(const SwParams p)
                         c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
                         if (tile > 0) bv = __ldcg(bnd_in + col);
                     }
-                    // lane 0 consumes entry `col` at step col and then adds ext: store with beta_{col-1}
-                    const uint32_t bb = (uint32_t)((col - 1 - tbase) * ext) * 65537u;
+                    // lane 0 consumes entry `col` at step col: store it with that step's bias beta_col
+                    const uint32_t bb = (uint32_t)((col - tbase) * ext) * 65537u;
                     bv.x += bb; bv.y += bb;
                     rring[col & (2 * kChunk - 1)] = c;
+                    rring[(col & (2 * kChunk - 1)) + 2 * kChunk] = c;
                     bring[col & (kChunk - 1)] = bv;
                 }
                 __syncwarp();
@@ -332,6 +368,7 @@ sw_wavefront_kernel(const SwParams p)
             }
 
             // ---- tile epilogue: warp arg-best per half, merge into the running best (later tiles hold larger rows)
+            const uint32_t fl = flb + (uint32_t)(total_steps - 1) * p.ext2;     // floor of the last step
             int s = (int)(bestprev & 0xffffu) - (int)(fl & 0xffffu), c = col_lo, r = row_lo;
             if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
             warp_argbest(s, c, r);
