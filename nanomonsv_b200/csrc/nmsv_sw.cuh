@@ -30,6 +30,8 @@ constexpr int kRowPad = 6;         // row beyond the end of a template half: sco
 constexpr int kNumCodes = 5;       // A C G T wildcard
 constexpr int kPadScore = -128;
 constexpr int kChunk = 128;        // columns staged per refill
+constexpr int kRing = 4 * kChunk;  // read ring: the chunk in use, the previous one (lanes lag up to 31 columns) and
+                                   // the next one, which TMA fills while the current chunk is computed
 #ifndef NMSV_WPB
 #define NMSV_WPB 4
 #endif
@@ -84,7 +86,8 @@ __host__ __device__ constexpr size_t warp_smem_bytes()
          + (size_t)kChunk * 8                               // boundary ring (inputs of lane 0), uint2 per column
          + (size_t)32 * 8                                   // boundary staging (outputs of lane 31), one group
          + (size_t)16                                       // constant slot read by lanes 1..31 instead of the ring
-         + (size_t)4 * kChunk;                              // read ring, 1 byte per column, stored twice (mirrored)
+         + (size_t)16                                       // mbarrier of the TMA (cp.async.bulk) read staging
+         + (size_t)2 * kRing;                               // read ring (4 chunk slots), stored twice (mirrored)
 }
 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi)
@@ -113,6 +116,42 @@ __device__ __forceinline__ uint32_t add_halves(uint32_t x, int k)
     uint32_t r;
     asm("mad.lo.u32 %0, %1, 65537, %2;" : "=r"(r) : "r"((uint32_t)k), "r"(x));
     return r;
+}
+
+// ---- TMA (1-D bulk copy) staging of the read: global -> shared, completion on a per-warp mbarrier --------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// Potentially-blocking wait with a suspend-time hint. It is used WITHOUT a poll loop on purpose: a data-dependent
+// loop (like a mutable per-thread "in flight" flag) makes the compiler drop its convergence / uniformity assumptions
+// for the whole kernel (BRA.DIV before every shuffle, per-lane instead of uniform index arithmetic, +15 registers).
+// The copy waited for was issued a whole chunk (~10^5 cycles) earlier.
+__device__ __forceinline__ bool mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+
+// bytes must be a multiple of 16, src and dst 16-byte aligned
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 // lexicographic "better": higher score, then smaller column, then smaller row
@@ -144,7 +183,8 @@ sw_wavefront_kernel(const SwParams p)
     uint2* bring = reinterpret_cast<uint2*>(wbase + (size_t)kNumCodes * G * 32 * 16);
     uint2* bstage = bring + kChunk;
     uint2* bconst = bstage + 32;
-    uint8_t* rring = reinterpret_cast<uint8_t*>(bconst + 2);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(bconst + 2);
+    uint8_t* rring = reinterpret_cast<uint8_t*>(bconst + 4);
     const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + warp;
     uint2* const bnd0 = p.bnd + (size_t)gwarp * 2 * p.bnd_stride;
 
@@ -167,8 +207,14 @@ sw_wavefront_kernel(const SwParams p)
     const uint32_t m1 = is_lane0 ? 0u : 1u;
     const char* const bsrc = is_lane0 ? reinterpret_cast<const char*>(bring) : reinterpret_cast<const char*>(bconst);
     const uint32_t bstride = is_lane0 ? 8u : 0u;
-    // read ring: column j lives at rring[j & 255] and rring[(j & 255) + 256]; lane l reads (t & 255) + 256 - l
-    const uint8_t* const rlane = rring + 2 * kChunk - lane;
+    // read ring: column j lives at rring[j % kRing] and again kRing bytes later; lane l reads (t % kRing) + kRing - l
+    const uint8_t* const rlane = rring + kRing - lane;
+    if (lane == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t tma_parity = 0;       // phase of the next mbarrier completion to wait for
 
     for (;;) {
         uint32_t ti = 0;
@@ -215,7 +261,7 @@ sw_wavefront_kernel(const SwParams p)
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < (4 * kChunk) / 32; ++u) rring[u * 32 + lane] = (uint8_t)kPadCode;
+                for (int u = 0; u < (2 * kRing) / 32; ++u) rring[u * 32 + lane] = (uint8_t)kPadCode;
                 if (lane == 0) bconst[0] = make_uint2((uint32_t)(ext * 65537), (uint32_t)(ext * 65537));
             }
 
@@ -230,6 +276,9 @@ sw_wavefront_kernel(const SwParams p)
             int col_lo = 0, row_lo = 0, col_hi = 0, row_hi = 0;   // only meaningful once best rose above the floor
             uint32_t h_last = FLOOR0, f_out = EF0, diag = FLOOR0;
             int tbase = -1;          // beta_t = (t - tbase) * ext ; state "after step -1" carries beta = 0
+            // TMA staging applies to forward reads that start on a 16-byte boundary; whether a given chunk was
+            // prefetched is a pure function of t0 (a mutable flag would cost the compiler its uniformity analysis)
+            const bool tma_task = !c_rev && ((task.c_base & 15ull) == 0);
 
             const uint32_t MARGIN = (uint32_t)((p.open + 2 * ext) * 65537);   // open + 2*ext in both halves
             auto step = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const int t) {
@@ -244,7 +293,7 @@ sw_wavefront_kernel(const SwParams p)
                 uint32_t hin, fin;     // H / F of the row above this strip, lifted to this step's bias
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hin) : "r"(sh), "r"(m1), "r"(bv.x));
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(fin) : "r"(sf), "r"(m1), "r"(bv.y));
-                const uint32_t b = rlane[t & (2 * kChunk - 1)];
+                const uint32_t b = rlane[t & (kRing - 1)];
                 const uint4* pp = prof + b * (G * 32) + lane;
 
                 uint32_t S[4 * G];
@@ -312,21 +361,47 @@ sw_wavefront_kernel(const SwParams p)
                 }
                 // ---- refill: columns [t0, t0+kChunk) of the read ring and of the boundary ring
                 __syncwarp();
+                const bool prefetched = tma_task && t0 >= kChunk && t0 + kChunk <= ncols;   // issued one chunk ago
 #pragma unroll
                 for (int u = 0; u < kChunk / 32; ++u) {
                     const int col = t0 + u * 32 + lane;
                     uint8_t c = (uint8_t)kPadCode;
                     uint2 bv = make_uint2(FLOOR0, EF0);
                     if (col < ncols) {
-                        c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
+                        if (!prefetched)
+                            c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
                         if (tile > 0) bv = __ldcg(bnd_in + col);
                     }
                     // lane 0 consumes entry `col` at step col: store it with that step's bias beta_col
                     const uint32_t bb = (uint32_t)((col - tbase) * ext) * 65537u;
                     bv.x += bb; bv.y += bb;
-                    rring[col & (2 * kChunk - 1)] = c;
-                    rring[(col & (2 * kChunk - 1)) + 2 * kChunk] = c;
+                    if (!prefetched) {
+                        rring[col & (kRing - 1)] = c;
+                        rring[(col & (kRing - 1)) + kRing] = c;
+                    }
                     bring[col & (kChunk - 1)] = bv;
+                }
+                if (prefetched) {               // the bulk copies issued one chunk ago have landed?
+                    // votes make the outcome warp-uniform in the compiler's eyes
+                    bool landed = __all_sync(kFull, mbar_wait_hint(mbar, tma_parity, 1000000u));
+                    if (!landed) landed = __all_sync(kFull, mbar_wait_hint(mbar, tma_parity, 10000000u));
+                    if (!landed) landed = __all_sync(kFull, mbar_wait_hint(mbar, tma_parity, 100000000u));
+                    if (!landed) __trap();       // 256 bytes not delivered after > 100 ms: the device is broken
+                    tma_parity ^= 1u;
+                }
+                __syncwarp();
+                // ---- TMA prefetch of the NEXT chunk of the read into the free ring slot (twice: the ring is mirrored);
+                //      it lands while this chunk is computed. Needs 16-byte aligned addresses and a whole chunk; the
+                //      begin pass (reversed read) and ragged tails use the plain loads above.
+                if (tma_task && t0 + 2 * kChunk <= ncols) {
+                    if (lane == 0) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // order earlier LDS of that slot
+                        const uint8_t* src = p.codes + task.c_base + (uint64_t)(t0 + kChunk);
+                        uint8_t* dst = rring + ((t0 + kChunk) & (kRing - 1));
+                        mbar_expect_tx(mbar, 2 * kChunk);
+                        tma_load_1d(dst, src, kChunk, mbar);
+                        tma_load_1d(dst + kRing, src, kChunk, mbar);
+                    }
                 }
                 __syncwarp();
 

@@ -67,12 +67,18 @@ class SeqPack:
 
     def finalize(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         if self._frozen is None:
+            # every sequence starts on a 16-byte boundary (filled with the wildcard code): the kernel stages reads
+            # with 16-byte-granular bulk copies (TMA); unaligned offsets are legal but take the plain-load path
             lens = np.asarray(self._lens, dtype=np.uint32)
+            padded = (lens.astype(np.uint64) + np.uint64(15)) & ~np.uint64(15)
             offsets = np.zeros(len(lens), dtype=np.uint64)
             if len(lens) > 1:
-                np.cumsum(lens[:-1].astype(np.uint64), out=offsets[1:])
-            codes = np.concatenate(self._chunks) if self._chunks else np.zeros(0, dtype=np.uint8)
-            self._frozen = (np.ascontiguousarray(codes), offsets, lens)
+                np.cumsum(padded[:-1], out=offsets[1:])
+            total = int(offsets[-1] + padded[-1]) if len(lens) else 0
+            codes = np.full(total, 4, dtype=np.uint8)
+            for off, chunk in zip(offsets, self._chunks):
+                codes[int(off):int(off) + len(chunk)] = chunk
+            self._frozen = (codes, offsets, lens)
             self._chunks = []
         return self._frozen
 
