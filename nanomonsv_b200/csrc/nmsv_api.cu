@@ -823,7 +823,7 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
     CUDA_TRY(ctx, pl->records.alloc(sizeof(nmsv_record) * (uint64_t)n_reads, s));
     CUDA_TRY(ctx, pl->counters.alloc(sizeof(uint32_t) * kCntTotal, s));
     pl->bnd_stride = max_cols_multi ? max_cols_multi : 1;
-    const uint64_t bnd_bytes = max_cols_multi ? (uint64_t)max_grid_warps(ctx) * 2 * pl->bnd_stride * sizeof(uint2) : 16;
+    const uint64_t bnd_bytes = max_cols_multi ? (uint64_t)max_grid_warps(ctx) * pl->bnd_stride * sizeof(uint2) : 16;
     CUDA_TRY(ctx, pl->bnd.alloc(bnd_bytes, s));
     stt.workspace_bytes = pl->tasks.bytes + pl->fwd.bytes + pl->rev_tasks.bytes + pl->rev.bytes + pl->sel.bytes +
                           pl->alns.bytes + pl->flags.bytes + pl->supporting.bytes + pl->records.bytes + pl->bnd.bytes;
@@ -1069,7 +1069,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     CUDA_TRY(ctx, counters.alloc(sizeof(uint32_t) * kCntTotal, s));
     CUDA_TRY(ctx, cudaMemsetAsync(counters.p, 0, sizeof(uint32_t) * kCntTotal, s));
     const uint32_t stride = max_cols_multi ? max_cols_multi : 1;
-    CUDA_TRY(ctx, bnd.alloc(max_cols_multi ? (uint64_t)max_grid_warps(ctx) * 2 * stride * sizeof(uint2) : 16, s));
+    CUDA_TRY(ctx, bnd.alloc(max_cols_multi ? (uint64_t)max_grid_warps(ctx) * stride * sizeof(uint2) : 16, s));
     const size_t out_bytes = out_ssw ? sizeof(nmsv_ssw_result) * (size_t)n_pairs : sizeof(nmsv_aln) * (size_t)n_pairs;
     CUDA_TRY(ctx, d_out.alloc(out_bytes, s));
 

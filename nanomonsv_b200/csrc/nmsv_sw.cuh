@@ -68,7 +68,7 @@ struct SwParams {
     uint32_t n_tasks;
     uint32_t* queue_head;          // zeroed before the launch
     SwResult* results;
-    uint2* bnd;                    // [grid warps][2][bnd_stride] tile-boundary scratch
+    uint2* bnd;                    // [grid warps][bnd_stride] tile-boundary scratch (H, F of a tile's last row)
     uint32_t bnd_stride;
     int match, mismatch, open, ext;
     uint32_t neg_open2;     // (-open, -open) packed: DPX add operand, read from the constant bank
@@ -186,7 +186,7 @@ sw_wavefront_kernel(const SwParams p)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bconst + 2);
     uint8_t* rring = reinterpret_cast<uint8_t*>(bconst + 4);
     const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + warp;
-    uint2* const bnd0 = p.bnd + (size_t)gwarp * 2 * p.bnd_stride;
+    uint2* const bnd0 = p.bnd + (size_t)gwarp * p.bnd_stride;
 
     const uint32_t n_tasks = p.n_tasks_dev ? *p.n_tasks_dev : p.n_tasks;
     // Every stored H/E/F value is  true value + a + beta_t  with a = open + ext and beta_t = (t - tbase) * ext:
@@ -240,8 +240,10 @@ sw_wavefront_kernel(const SwParams p)
 
         for (int tile = 0; tile < ntiles; ++tile) {
             const int row0 = tile * 32 * R + lane * R;
-            uint2* const bnd_in = bnd0 + (size_t)((tile + 1) & 1) * p.bnd_stride;
-            uint2* const bnd_out = bnd0 + (size_t)(tile & 1) * p.bnd_stride;
+            // One boundary buffer per warp, updated in place: tile q reads column c of the row above it at the refill of
+            // the chunk containing c (step <= c) and writes its own last row for column c at the flush after step c+31.
+            uint2* const bnd_in = bnd0;
+            uint2* const bnd_out = bnd0;
             const bool write_bnd = (tile + 1 < ntiles);
             const bool stage_lane = write_bnd && lane == 31;
 
