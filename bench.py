@@ -328,7 +328,7 @@ def main():
             "dpx_lane_inst_per_cell": DPX_PER_CELL,
             "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / step_kernel_ms,
             "gcups_kernel": st["cells_executed"] / (dom_ms * 1e-3) / 1e9,
-            "traffic": None,
+            "traffic": _traffic(st["cells_executed"]),
             "hbm": {"algorithmic_bytes": int(codes.size), "achieved_gbs": codes.size / (dom_ms * 1e-3) / 1e9,
                     "peak_gbs": _measured_peaks().get("hbm_gbs"), "note": "HBM is 3-4 orders of magnitude off the critical path"},
             "launches_ms": [{"kernel": n, "R": r, "ms": round(ms, 4)} for n, r, ms in ktimes],
@@ -370,6 +370,17 @@ def main():
     plan.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _traffic(cells_executed: float):
+    """DRAM bytes of the forward launch: ncu capture under profiles/, scaled by the executed cells of this batch
+    (the traffic is the per-column tile-boundary spill, proportional to the cells). None if the capture is absent."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
+        return {"dram_bytes_per_launch": t["dram_bytes_per_executed_cell"] * cells_executed,
+                "source": t["source"] + ", scaled by executed cells"}
+    except Exception:   # noqa: BLE001
+        return None
 
 
 def _measured_peaks() -> dict:
