@@ -38,6 +38,10 @@ sys.path.insert(0, ROOT)
 # the sampled running maximum = 66 instructions per 32 cells (SASS count)
 DPX_PER_CELL = 66.0 / 32.0
 WORKLOAD = "colo829_shaped"
+# mean EXECUTED forward cells of one synthetic candidate (tumor + control reads, both strands, m = 2000, identical
+# templates counted once), measured on the generator; the per-GPU batch is cut at --svs-per-gpu times this budget so
+# that every rank does equal device work
+CELLS_PER_CANDIDATE = 7.926e9
 
 
 def log(*a):
@@ -65,17 +69,33 @@ def build_batch(n_sv: int, rank: int, args):
     cfg = dataclasses.replace(synth.PRESETS[WORKLOAD], seed=synth.PRESETS[WORKLOAD].seed + 7919 * rank,
                               contig_len=4_000_000, n_contigs=4)
     t0 = time.time()
-    wl = synth.make_workload(cfg, n_sv)
+    # weak scaling needs equal work per rank: draw some spare candidates and keep the first ones (in generation
+    # order) whose reference-equivalent cell count reaches the per-GPU budget of n_sv average candidates
+    spare = max(8, n_sv // 5)
+    wl = synth.make_workload(cfg, n_sv + spare)
     L = cfg.validate_sequence_length
+    per_sv = []
+    for i, sv in enumerate(wl.svs):
+        bases = sum(len(r.codes) for smp in ("tumor", "control") for r in wl.samples[smp][i])
+        v1, v2, r1, r2, short = canonical_templates(sv.key, wl.fasta, L)
+        distinct = {v1, v2} | ({r1, r2} if short else set())     # identical templates are aligned once on the GPU
+        per_sv.append(2 * sum(len(t) for t in distinct) * bases)
+    budget = CELLS_PER_CANDIDATE * n_sv
+    keep, acc = [], 0
+    for i, c in enumerate(per_sv):
+        if acc >= budget:
+            break
+        keep.append(i); acc += c
+    keep_set = set(keep)
     bb = BatchBuilder(score_ratio_thres=1.2, var_read_min_mapq=0)
     for sample in ("tumor", "control"):
-        for i in wl.sv_order():
+        for i in [j for j in wl.sv_order() if j in keep_set]:
             var1, var2, ref1, ref2, short = canonical_templates(wl.svs[i].key, wl.fasta, L)
             bb.add_sv([var1, var2, ref1 if short else None, ref2 if short else None], False, short)
             for rd in wl.samples[sample][i]:
                 bb.add_read(rd.codes, rd.mapq1, rd.mapq2)
     pack, svs, reads = bb.finalize()
-    log(f"[rank {rank}] synthetic batch: {n_sv} candidates x (tumor, control), {len(reads)} reads, "
+    log(f"[rank {rank}] synthetic batch: {len(keep)} candidates x (tumor, control), {len(reads)} reads, "
         f"{pack.finalize()[0].size / 1e6:.0f} MB of bases, built in {time.time() - t0:.1f}s")
     return cfg, pack, svs, reads
 
@@ -250,26 +270,37 @@ def main():
     plan = eng.plan(pack, svs, reads)
     plan.set_profiling(True)
     st = plan.stats()
-    counts = torch.zeros(len(svs) * max(world, 1), dtype=torch.int32, device=dev)
-    my_slice = counts[rank * len(svs):(rank + 1) * len(svs)]
+    # the path's only exchange: ONE merge of the per-GPU supporting-read count tables at the end of the job
+    # (NCCL all-reduce of a dense int32 table over NVLink); the job here = the timed steps
+    cap = len(svs) + 64
+    n_max = torch.tensor([len(svs)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
+    cap = int(n_max.item())
+    counts = torch.zeros((args.steps, max(world, 1), cap), dtype=torch.int32, device=dev)
 
-    def step():
+    def step(k):
         plan.run()
-        if world > 1:   # the path's only exchange: merge the per-GPU supporting-read counts (NCCL over NVLink)
-            plan.copy_counts_to_device(my_slice.data_ptr())
+        if world > 1:
+            plan.copy_counts_to_device(counts[k, rank].data_ptr())
+
+    def final_gather():
+        if world > 1:
             dist.all_reduce(counts)
-            counts.zero_()
 
     for _ in range(args.warmup):
-        step()
+        step(0)
+    final_gather()
+    counts.zero_()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
-        step()
+    for k in range(args.steps):
+        step(k)
+    final_gather()
     e1.record(stream)
     barrier()
     ms_step = e0.elapsed_time(e1) / args.steps
@@ -283,21 +314,20 @@ def main():
     hpack = SeqPack.from_arrays(pin(codes), pin(offsets), pin(lens))
     hsvs, hreads = pin(svs.view(np.uint8)).view(svs.dtype), pin(reads.view(np.uint8)).view(reads.dtype)
 
-    def e2e_step():
+    def e2e_step(k):
         c, s, r = eng.validate(hpack, hsvs, hreads)
         if world > 1:
-            t = torch.from_numpy(np.ascontiguousarray(s)).to(dev, non_blocking=True)
-            counts[rank * len(svs):(rank + 1) * len(svs)] = t
-            dist.all_reduce(counts)
-            counts.zero_()
+            counts[k, rank, :len(s)] = torch.from_numpy(np.ascontiguousarray(s)).to(dev, non_blocking=True)
         return s, r
 
+    counts.zero_()
     for _ in range(2):
-        e2e_step()
+        e2e_step(0)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        s_e2e, r_e2e = e2e_step()
+    for k in range(args.steps):
+        s_e2e, r_e2e = e2e_step(k)
+    final_gather()
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
@@ -342,7 +372,7 @@ def main():
                        "sv_candidates_per_gpu_per_step": n_cand, "reads_per_gpu_per_step": int(len(reads)),
                        "read_bases_per_gpu_mb": round(codes.size / 1e6, 1),
                        "l2": f"inputs ({codes.size / 1e6:.0f} MB of read bases per GPU) exceed the {info['l2_bytes'] / 1e6:.0f} MB L2",
-                       "parallelism": f"sv-shards x{world}, one NCCL all-reduce of the count table per step" if world > 1 else "single GPU"},
+                       "parallelism": f"sv-shards x{world}, equal cell budget per GPU, one NCCL all-reduce of the count tables at the end of the job" if world > 1 else "single GPU"},
             "sv_per_s": cand_total / (ms_step * 1e-3),
             "gcups_executed": cells_exec / (ms_step * 1e-3) / 1e9,
             "cells_reference_per_step": cells_ref, "cells_executed_per_step": cells_exec,
