@@ -230,7 +230,7 @@ sw_wavefront_kernel(const SwParams p)
         const bool c_rev = task.flags & kCRev;
         const int rows = a_len > b_len ? a_len : b_len;
         const int ntiles = (rows + 32 * R - 1) / (32 * R);
-        const int total_steps = (ncols + 31 + 1) & ~1;   // even: the step body is unrolled twice (a pad step is inert)
+        const int total_steps = (ncols + 31 + 3) & ~3;   // multiple of 4: the step body is unrolled 4x (pad steps are inert)
         // steps the bias may run before the 16-bit lanes could overflow (host guarantees >= kChunk)
         const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext : 0x7fffffff;
 
@@ -282,33 +282,27 @@ sw_wavefront_kernel(const SwParams p)
             // prefetched is a pure function of t0 (a mutable flag would cost the compiler its uniformity analysis)
             const bool tma_task = !c_rev && ((task.c_base & 15ull) == 0);
 
-            const uint32_t MARGIN = (uint32_t)((p.open + 2 * ext) * 65537);   // open + 2*ext in both halves
-            auto step = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const int t) {
-                const uint32_t fl = flb + (uint32_t)t * p.ext2;    // floor of this step: warp-uniform
-#ifdef NMSV_EXP_NO_SHFL
-                const uint32_t sh = h_last, sf = f_out;
-#else
+            // Filter threshold for TWO consecutive columns at once: no row of either column exceeds the running maximum
+            // if no sampled row comes within open + 2*ext of it; the older column is compared one ext too strictly.
+            const uint32_t MARGIN2 = (uint32_t)((p.open + 3 * ext) * 65537);
+            // One column. tq = t - U is a multiple of 4, so every ring index of step t is a base computed once per four
+            // steps plus the compile-time constant U (no per-step uniform-datapath arithmetic).
+            auto column = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const uint32_t fl, const char* bq,
+                              const uint8_t* rq, uint2* sq, const int U) {
                 const uint32_t sh = __shfl_up_sync(kFull, h_last, 1);
                 const uint32_t sf = __shfl_up_sync(kFull, f_out, 1);
-#endif
-                const uint2 bv = *reinterpret_cast<const uint2*>(bsrc + (uint32_t)(t & (kChunk - 1)) * bstride);
+                const uint2 bv = *reinterpret_cast<const uint2*>(bq + (uint32_t)U * bstride);
                 uint32_t hin, fin;     // H / F of the row above this strip, lifted to this step's bias
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hin) : "r"(sh), "r"(m1), "r"(bv.x));
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(fin) : "r"(sf), "r"(m1), "r"(bv.y));
-                const uint32_t b = rlane[t & (kRing - 1)];
+                const uint32_t b = rq[U];
                 const uint4* pp = prof + b * (G * 32) + lane;
-
                 uint32_t S[4 * G];
-#ifdef NMSV_EXP_NO_LDS
-#pragma unroll
-                for (int g = 0; g < 4 * G; ++g) S[g] = (uint32_t)(size_t)pp + g;
-#else
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const uint4 v = pp[g * 32];
                     S[4 * g + 0] = v.x; S[4 * g + 1] = v.y; S[4 * g + 2] = v.z; S[4 * g + 3] = v.w;
                 }
-#endif
                 uint32_t F = fin;
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
@@ -322,31 +316,48 @@ sw_wavefront_kernel(const SwParams p)
                 diag = hin;
                 h_last = Hd[R - 1];
                 f_out = F;
-                if (stage_lane) bstage[t & 31] = make_uint2(h_last, f_out);
-
-                // ---- running maximum. Rows k and k' <= k of one column satisfy H[k] >= H[k'] - open - (k-k'-1)*ext
-                // (through F), so if no row of {R-1, R-5, ...} comes within open + 2*ext of the running maximum,
-                // no row of the strip exceeds it: 1 DPX per 8 rows instead of 1 per 2 rows in the common case.
-                const uint32_t bp = add_halves(bestprev, ext);
-                const uint32_t bpm = bp - MARGIN;                    // fl >= open + 2*ext: no borrow
-                uint32_t q = bpm;
+                if (stage_lane) sq[U] = make_uint2(h_last, f_out);
+            };
+            // ---- running maximum after a pair of columns (older column in Ha, newer in Hb; t = step of the older).
+            // Rows k and k' <= k of one column satisfy H[k] >= H[k'] - open - (k-k'-1)*ext (through F), so if no row
+            // of {R-1, R-5, ...} comes within the margin of the running maximum no row of the strip exceeds it:
+            // 1 DPX per 8 rows and column instead of 1 per 2 rows in the common case.
+            auto track = [&](const uint32_t (&Ha)[R], const uint32_t (&Hb)[R], const int t) {
+                const uint32_t bp2 = add_halves(bestprev, 2 * ext);      // running maximum at the newer column's bias
+                const uint32_t thr = bp2 - MARGIN2;                       // floors >= open + 2*ext: no borrow
+                uint32_t q = thr;
 #pragma unroll
-                for (int k = R - 1; k >= 0; k -= 8) q = __vimax3_s16x2(q, Hd[k], Hd[k >= 4 ? k - 4 : k]);
-                uint32_t best = bp;
-                if (q != bpm) {
-                    // rare: some row may exceed this lane's running maximum. One prefix-maximum pass: VIMNMX with
-                    // predicate outputs tells per half whether H[k] strictly beats everything before it; the last
-                    // such row is the first row holding the column maximum (parasail: smallest row).
+                for (int k = R - 1; k >= 0; k -= 8) {
+                    q = __vimax3_s16x2(q, Ha[k], Ha[k >= 4 ? k - 4 : k]);
+                    q = __vimax3_s16x2(q, Hb[k], Hb[k >= 4 ? k - 4 : k]);
+                }
+                uint32_t best = bp2;
+                if (q != thr) {
+                    // rare: some row may exceed this lane's running maximum. One prefix-maximum pass per column: VIMNMX
+                    // with predicate outputs tells per half whether H[k] strictly beats everything before it; the
+                    // last such row is the first row holding the column maximum (parasail: smallest row).
+                    best = add_halves(bestprev, ext);
                     int rl = -1, rh = -1;
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         bool keep_hi, keep_lo;                       // keep_* = (best >= H[k]) in that half
-                        best = __vibmax_s16x2(best, Hd[k], &keep_hi, &keep_lo);
+                        best = __vibmax_s16x2(best, Ha[k], &keep_hi, &keep_lo);
                         if (!keep_lo) rl = k;
                         if (!keep_hi) rh = k;
                     }
                     if (rl >= 0) { col_lo = t - lane; row_lo = row0 + rl; }
                     if (rh >= 0) { col_hi = t - lane; row_hi = row0 + rh; }
+                    best = add_halves(best, ext);
+                    rl = -1; rh = -1;
+#pragma unroll
+                    for (int k = 0; k < R; ++k) {
+                        bool keep_hi, keep_lo;
+                        best = __vibmax_s16x2(best, Hb[k], &keep_hi, &keep_lo);
+                        if (!keep_lo) rl = k;
+                        if (!keep_hi) rh = k;
+                    }
+                    if (rl >= 0) { col_lo = t + 1 - lane; row_lo = row0 + rl; }
+                    if (rh >= 0) { col_hi = t + 1 - lane; row_hi = row0 + rh; }
                 }
                 bestprev = best;
             };
@@ -410,9 +421,17 @@ sw_wavefront_kernel(const SwParams p)
                 const int t1 = (t0 + kChunk < total_steps) ? t0 + kChunk : total_steps;
                 for (int g0 = t0; g0 < t1; g0 += 32) {
                     const int g1 = (g0 + 32 < t1) ? g0 + 32 : t1;     // g1 - g0 is even (total_steps is even)
-                    for (int t = g0; t < g1; t += 2) {
-                        step(HA, HB, t);
-                        step(HB, HA, t + 1);
+                    for (int t = g0; t < g1; t += 4) {        // g0, g1 and total_steps are multiples of 4
+                        const uint32_t fl = flb + (uint32_t)t * p.ext2;        // floor of step t: warp-uniform
+                        const char* bq = bsrc + (uint32_t)(t & (kChunk - 1)) * bstride;
+                        const uint8_t* rq = rlane + (t & (kRing - 1));
+                        uint2* sq = bstage + (t & 31);
+                        column(HA, HB, fl, bq, rq, sq, 0);
+                        column(HB, HA, fl + p.ext2, bq, rq, sq, 1);
+                        track(HB, HA, t);
+                        column(HA, HB, fl + 2 * p.ext2, bq, rq, sq, 2);
+                        column(HB, HA, fl + 3 * p.ext2, bq, rq, sq, 3);
+                        track(HB, HA, t + 2);
                     }
                     // ---- event filter: only a cell that reaches the final maximum of the whole alignment matters, and
                     //      any H seen so far is a lower bound of it. Lift every lane's running maximum to (warp-wide
