@@ -29,7 +29,7 @@ _LIB_PATH = os.path.join(_HERE, "libnmsv_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the C oracle with gcc (oracle/Makefile). Returns the path of the shared library."""
-    srcs = [os.path.join(_HERE, f) for f in ("nmsv_oracle.c", "nmsv_striped.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("nmsv_oracle.c", "nmsv_striped.c", "nmsv_jump_oracle.c")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
@@ -44,6 +44,12 @@ class SswResult(ctypes.Structure):
 
     def astuple(self) -> Tuple[int, int, int, int, int]:
         return (self.score1, self.read_begin1, self.read_end1, self.ref_begin1, self.ref_end1)
+
+
+class JumpResult(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("found", "score", "i1_start", "i1_end", "i2_start", "i2_end", "j1_start",
+                                              "j1_end", "j2_start", "j2_end")] + \
+               [("n_ops2", ctypes.c_uint32), ("n_ops1", ctypes.c_uint32)]
 
 
 _lib = None
@@ -72,6 +78,9 @@ def lib():
                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
         L.ora_striped_ssw_batch.restype = ctypes.c_int
         L.ora_have_avx2.restype = ctypes.c_int
+        L.ora_sw_jump.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(JumpResult), vp]
+        L.ora_sw_jump.restype = ctypes.c_int
         _lib = L
     return _lib
 
@@ -364,3 +373,55 @@ def count_from_seam(seam_path: str, fasta, output_count_file: str, output_info_f
                 cur_key, rows = key, []
             rows.append((rid, m1, m2, seq))
         flush()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# "next" row: smith_waterman.sw_jump (reference nanomonsv/smith_waterman.py:5-127)
+# ----------------------------------------------------------------------------------------------------------------
+def jump_strings(contig: str, region1: str, region2: str, res, ops: np.ndarray):
+    """Rebuild the two alignment strings of sw_jump's return value (:61-125) from the traceback operations."""
+    c2, g2 = [], []
+    i, j = res["i2_end"], res["j2_end"]
+    for p in ops[:res["n_ops2"]]:
+        if p == 1:
+            c2.append(contig[i - 1]); g2.append(region2[j - 1]); i -= 1; j -= 1
+        elif p == 2:
+            c2.append(contig[i - 1]); g2.append("-"); i -= 1
+        elif p == 3:
+            c2.append("-"); g2.append(region2[j - 1]); j -= 1
+        elif p == 4:
+            c2.append(contig[i - 1]); g2.append(region2[j - 1])
+    c1, g1 = [], []
+    i, j = res["i1_end"], res["j1_end"]
+    for p in ops[res["n_ops2"]:res["n_ops2"] + res["n_ops1"]]:
+        if p == 1:
+            c1.append(contig[i - 1]); g1.append(region1[j - 1]); i -= 1; j -= 1
+        elif p == 2:
+            c1.append(contig[i - 1]); g1.append("-"); i -= 1
+        elif p == 3:
+            c1.append("-"); g1.append(region1[j - 1]); j -= 1
+    return "".join(reversed(c1)) + " " + "".join(reversed(c2)), "".join(reversed(g1)) + " " + "".join(reversed(g2))
+
+
+def sw_jump(contig: str, region1_seq: str, region2_seq: str, match_score: int = 1, mismatch_penalty: int = 2,
+            gap_cost: int = 2, jump_cost: int = 2, minimum_score: int = 10):
+    """smith_waterman.sw_jump with the same return value (None or the 6-tuple), computed by the C oracle."""
+    L = lib()
+    c = np.frombuffer(contig.encode("latin-1"), dtype=np.uint8)
+    a = np.frombuffer(region1_seq.encode("latin-1"), dtype=np.uint8)
+    b = np.frombuffer(region2_seq.encode("latin-1"), dtype=np.uint8)
+    with np.errstate(divide="ignore"):
+        logtab = np.log(np.arange(len(c) + 1))
+    res = JumpResult()
+    ops = np.zeros(2 * len(c) + len(a) + len(b) + 4, dtype=np.uint8)
+    rc = L.ora_sw_jump(c.ctypes.data, len(c), a.ctypes.data, len(a), b.ctypes.data, len(b), match_score,
+                       mismatch_penalty, gap_cost, jump_cost, minimum_score, logtab.ctypes.data, ctypes.byref(res),
+                       ops.ctypes.data)
+    if rc != 0:
+        raise MemoryError("oracle allocation failure")
+    if not res.found:
+        return None
+    d = {n: getattr(res, n) for n, _ in JumpResult._fields_}
+    cm, rm = jump_strings(contig, region1_seq, region2_seq, d, ops)
+    return (res.score, (res.i1_start, res.i1_end, res.i2_start, res.i2_end), (res.j1_start, res.j1_end),
+            (res.j2_start, res.j2_end), cm, rm)

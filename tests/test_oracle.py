@@ -112,3 +112,16 @@ def test_validate_fixture_is_reproduced_by_the_oracle(tmp_path):
                           engine="striped")
         assert open(str(seam) + ".count").read().splitlines() == d["count"]
         assert sorted(open(str(seam) + ".info").read().splitlines()) == d["info"]
+
+
+def test_sw_jump_oracle_equals_reference_vectors():
+    """The vectors were produced by the reference's own smith_waterman.sw_jump (tests/golden/make_golden_jump.py)."""
+    vec = json.load(open(os.path.join(GOLDEN, "sw_jump_vectors.json")))["vectors"]
+    assert len(vec) > 100 and any(v["expected"] is None for v in vec)
+    for v in vec:
+        got = O.sw_jump(v["contig"], v["region1"], v["region2"], *v["params"])
+        exp = v["expected"]
+        if exp is None:
+            assert got is None
+        else:
+            assert [got[0], list(got[1]), list(got[2]), list(got[3]), got[4], got[5]] == exp
