@@ -195,6 +195,35 @@ int nmsv_plan_copy_counts_device(nmsv_plan *plan, void *d_supporting_int32);
 int nmsv_plan_download_alns(nmsv_plan *plan, nmsv_aln *alns, uint8_t *read_flags);
 void nmsv_plan_destroy(nmsv_plan *plan);
 
+/* ---- "next" row: breakpoint refinement DP, smith_waterman.sw_jump -------------------------------------------------- */
+/* Replaces nanomonsv/smith_waterman.py:5-127 (sw_jump), called from nanomonsv/locate_bp.py:37,67: two linear-gap DP
+ * matrices (contig x region1, contig x region2) where the second may jump from the best row of the first at a cost of
+ * jump_cost * ln(distance), followed by the traceback. Sequences are RAW BYTES here (the reference compares
+ * characters, so 'N' matches 'N' and case matters); bytes/offsets/lens use the same one-buffer layout as above.   */
+typedef struct {
+    int32_t match_score, mismatch_penalty, gap_cost, jump_cost, minimum_score;   /* sw_jump defaults: 1, 2, 2, 2, 10 */
+} nmsv_jump_params;
+
+typedef struct {
+    int32_t found;                 /* 0: the reference returns None */
+    int32_t score;                 /* H2.max() */
+    int32_t i1_start, i1_end, i2_start, i2_end;   /* contig coordinates of the two aligned fragments (as returned) */
+    int32_t j1_start, j1_end;      /* region1 */
+    int32_t j2_start, j2_end;      /* region2 */
+    uint32_t n_ops2, n_ops1;       /* traceback operations written to `ops`: H2 part then H1 part, codes 1 = diagonal,
+                                      2 = contig base against a gap, 3 = region base against a gap, 4 = the jump cell */
+} nmsv_jump_result;
+
+/* ops of problem p start at sum over q < p of (2*n_q + m1_q + m2_q + 4) bytes (n = contig length, m = region
+ * lengths); ops_capacity must cover the sum over all problems. log_table[d] = ln(d) for d < log_table_len may be
+ * supplied by the caller (numpy's log in the Python layer, so that results are bit-identical to the reference);
+ * distances beyond the table use the C library's log. */
+int nmsv_sw_jump_batch(nmsv_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, const uint64_t *offsets,
+                       const uint32_t *lens, uint32_t n_seqs, const uint32_t *contig_idx, const uint32_t *region1_idx,
+                       const uint32_t *region2_idx, uint32_t n_problems, const nmsv_jump_params *params,
+                       const double *log_table, uint32_t log_table_len, nmsv_jump_result *out, uint8_t *ops,
+                       uint64_t ops_capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,16 @@ class Scoring(ctypes.Structure):
                 ("gap_extend", ctypes.c_int32)]
 
 
+class JumpParams(ctypes.Structure):
+    _fields_ = [("match_score", ctypes.c_int32), ("mismatch_penalty", ctypes.c_int32), ("gap_cost", ctypes.c_int32),
+                ("jump_cost", ctypes.c_int32), ("minimum_score", ctypes.c_int32)]
+
+
+JUMP_RESULT_DTYPE = np.dtype([(n, "<i4") for n in ("found", "score", "i1_start", "i1_end", "i2_start", "i2_end",
+                                                   "j1_start", "j1_end", "j2_start", "j2_end")] +
+                             [("n_ops2", "<u4"), ("n_ops1", "<u4")])
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("cells_reference", ctypes.c_uint64), ("cells_executed", ctypes.c_uint64),
                 ("cells_padded", ctypes.c_uint64), ("fwd_tasks", ctypes.c_uint64), ("rev_tasks", ctypes.c_uint64),
@@ -51,7 +61,7 @@ EXPORTS = ["nmsv_abi_version", "nmsv_create", "nmsv_destroy", "nmsv_last_error",
            "nmsv_device_info", "nmsv_encode_ascii", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
            "nmsv_plan_create", "nmsv_plan_run", "nmsv_plan_download", "nmsv_plan_stats", "nmsv_plan_download_alns",
            "nmsv_plan_destroy", "nmsv_plan_set_profiling", "nmsv_plan_kernel_times", "nmsv_plan_copy_counts_device",
-           "nmsv_measure_dpx_peak"]
+           "nmsv_measure_dpx_peak", "nmsv_sw_jump_batch"]
 
 _lib = None
 
@@ -120,5 +130,8 @@ def load() -> ctypes.CDLL:
     L.nmsv_plan_copy_counts_device.restype = ctypes.c_int
     L.nmsv_measure_dpx_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.nmsv_measure_dpx_peak.restype = ctypes.c_int
+    L.nmsv_sw_jump_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, vp, vp, u32, ctypes.POINTER(JumpParams), vp, u32, vp,
+                                     vp, u64]
+    L.nmsv_sw_jump_batch.restype = ctypes.c_int
     _lib = L
     return L

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libnmsv_sw.so")
 SOURCES = ["nmsv_api.cu"]
-HEADERS = ["nmsv_sw.cuh", os.path.join("..", "..", "include", "nmsv.h")]
+HEADERS = ["nmsv_sw.cuh", "nmsv_jump.cuh", os.path.join("..", "..", "include", "nmsv.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

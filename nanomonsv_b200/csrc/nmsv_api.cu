@@ -19,6 +19,7 @@
 
 #include "../../include/nmsv.h"
 #include "nmsv_sw.cuh"
+#include "nmsv_jump.cuh"
 
 using namespace nmsv;
 
@@ -1130,4 +1131,100 @@ extern "C" int nmsv_ssw_check_batch(nmsv_ctx* ctx, const uint8_t* codes, uint64_
 {
     return run_pairs(ctx, codes, n_codes, offsets, lens, n_seqs, tmpl_idx, tmpl_rc_idx, read_idx, n_pairs, scoring, 1,
                      1, nullptr, out);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// "next" row: sw_jump (reference smith_waterman.py:5-127)
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* offsets,
+                                  const uint32_t* lens, uint32_t n_seqs, const uint32_t* contig_idx,
+                                  const uint32_t* region1_idx, const uint32_t* region2_idx, uint32_t n_problems,
+                                  const nmsv_jump_params* params, const double* log_table, uint32_t log_table_len,
+                                  nmsv_jump_result* out, uint8_t* ops, uint64_t ops_capacity)
+{
+    static_assert(sizeof(nmsv_jump_result) == sizeof(JumpResult), "result layouts must match");
+    if (!ctx) return NMSV_E_INVALID;
+    if (n_problems == 0) return NMSV_OK;
+    if (!params || !contig_idx || !region1_idx || !region2_idx || !out || !ops)
+        return set_err(ctx, NMSV_E_INVALID, "nmsv_sw_jump_batch: NULL argument");
+    int rc = check_seq_tables(ctx, bytes, n_bytes, offsets, lens, n_seqs);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+
+    std::vector<JumpProblem> probs(n_problems);
+    uint64_t ops_total = 0;
+    uint32_t max_region = 0;
+    for (uint32_t i = 0; i < n_problems; ++i) {
+        const uint32_t c = contig_idx[i], a = region1_idx[i], b = region2_idx[i];
+        if (c >= n_seqs || a >= n_seqs || b >= n_seqs)
+            return set_err(ctx, NMSV_E_INVALID, "sw_jump problem %u: sequence index out of range", i);
+        if (lens[a] > (uint32_t)kJumpMaxRegion || lens[b] > (uint32_t)kJumpMaxRegion)
+            return set_err(ctx, NMSV_E_RANGE, "sw_jump problem %u: region longer than %d", i, kJumpMaxRegion);
+        JumpProblem& p = probs[i];
+        p.c_off = offsets[c]; p.r1_off = offsets[a]; p.r2_off = offsets[b];
+        p.n = lens[c]; p.m1 = lens[a]; p.m2 = lens[b]; p.pad = 0;
+        p.ops_off = ops_total;
+        ops_total += 2ull * p.n + p.m1 + p.m2 + 4;
+        max_region = std::max(max_region, std::max(p.m1, p.m2));
+    }
+    if (ops_total > ops_capacity)
+        return set_err(ctx, NMSV_E_CAPACITY, "ops buffer holds %llu bytes, %llu needed", (unsigned long long)ops_capacity,
+                       (unsigned long long)ops_total);
+
+    const size_t smem = 3ull * (max_region + 2) * sizeof(int32_t);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(sw_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    int bps = 0;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sw_jump_kernel, kJumpThreads, smem));
+    const uint32_t max_blocks = (uint32_t)ctx->prop.multiProcessorCount * (uint32_t)std::max(1, bps);
+
+    DevBuf d_bytes, d_log, d_probs, d_paths, d_rows, d_res, d_ops;
+    CUDA_TRY(ctx, d_bytes.alloc(n_bytes, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_bytes.p, bytes, n_bytes, cudaMemcpyHostToDevice, s));
+    if (log_table && log_table_len) {
+        CUDA_TRY(ctx, d_log.alloc(sizeof(double) * log_table_len, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_log.p, log_table, sizeof(double) * log_table_len, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(ctx, d_res.alloc(sizeof(JumpResult) * (size_t)n_problems, s));
+    CUDA_TRY(ctx, d_ops.alloc(ops_total, s));
+
+    // process the problems in chunks whose path workspace stays below ~6 GB
+    const uint64_t kMaxPathBytes = 6ull << 30;
+    uint32_t first = 0;
+    while (first < n_problems) {
+        uint64_t path_bytes = 0, row_words = 0;
+        uint32_t last = first;
+        while (last < n_problems) {
+            JumpProblem& p = probs[last];
+            const uint64_t pb = (uint64_t)(p.n + 1) * (p.m1 + 1) + (uint64_t)(p.n + 1) * (p.m2 + 1);
+            if (last > first && path_bytes + pb > kMaxPathBytes) break;
+            p.p1_off = path_bytes;
+            p.p2_off = path_bytes + (uint64_t)(p.n + 1) * (p.m1 + 1);
+            path_bytes += pb;
+            p.row_off = row_words;
+            row_words += 3ull * (p.n + 1) + ((uint64_t)p.n + p.m2 + 3) / 2 + 1;
+            ++last;
+        }
+        const uint32_t cnt = last - first;
+        CUDA_TRY(ctx, d_paths.alloc(path_bytes, s));
+        CUDA_TRY(ctx, d_rows.alloc(row_words * 8, s));
+        CUDA_TRY(ctx, d_probs.alloc(sizeof(JumpProblem) * (size_t)cnt, s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_probs.p, probs.data() + first, sizeof(JumpProblem) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+        JumpParams jp;
+        jp.bytes = d_bytes.as<uint8_t>(); jp.problems = d_probs.as<JumpProblem>(); jp.n_problems = cnt;
+        jp.paths = d_paths.as<uint8_t>(); jp.rows = d_rows.as<unsigned long long>();
+        jp.logtab = d_log.as<double>(); jp.logtab_len = (log_table && log_table_len) ? log_table_len : 0;
+        jp.results = d_res.as<JumpResult>() + first; jp.ops = d_ops.as<uint8_t>();
+        jp.match = params->match_score; jp.mismatch_penalty = params->mismatch_penalty; jp.gap_cost = params->gap_cost;
+        jp.jump_cost = params->jump_cost; jp.minimum_score = params->minimum_score;
+        sw_jump_kernel<<<std::min(cnt, max_blocks), kJumpThreads, smem, s>>>(jp);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));      // the host-side problem table of this chunk may be reused
+        first = last;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, d_res.p, sizeof(JumpResult) * (size_t)n_problems, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ops, d_ops.p, ops_total, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    return NMSV_OK;
 }

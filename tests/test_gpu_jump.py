@@ -1,0 +1,91 @@
+"""GPU parity tests of the sw_jump row (reference nanomonsv/smith_waterman.py:5-127): the CUDA path through
+nmsv_sw_jump_batch against (a) vectors produced by the reference's own function, (b) the C oracle on larger seeded
+problems of the shapes locate_bp.get_refined_bp creates (locate_bp.py:21-96)."""
+import json
+import os
+import random
+
+import pytest
+
+from nanomonsv_b200 import smith_waterman as SW
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_reference_vectors(engine):
+    vec = json.load(open(os.path.join(GOLDEN, "sw_jump_vectors.json")))["vectors"]
+    by_params = {}
+    for v in vec:
+        by_params.setdefault(tuple(v["params"]), []).append(v)
+    n_found = 0
+    for prm, vs in by_params.items():
+        got = SW.sw_jump_batch([(v["contig"], v["region1"], v["region2"]) for v in vs], *prm, engine=engine)
+        for v, g in zip(vs, got):
+            if v["expected"] is None:
+                assert g is None
+            else:
+                assert [g[0], list(g[1]), list(g[2]), list(g[3]), g[4], g[5]] == v["expected"]
+                n_found += 1
+    assert n_found > 80
+    one = vec[0]
+    g = SW.sw_jump(one["contig"], one["region1"], one["region2"], *one["params"], engine=engine)
+    assert [g[0], list(g[1]), list(g[2]), list(g[3]), g[4], g[5]] == one["expected"]
+
+
+def _junction_problem(rnd, n_flank, m1, m2, ins, err):
+    alpha = "ACGT"
+    r1 = "".join(rnd.choice(alpha) for _ in range(m1))
+    r2 = "".join(rnd.choice(alpha) for _ in range(m2))
+    core = r1[rnd.randint(0, 8):m1 - rnd.randint(0, 8)] + "".join(rnd.choice(alpha) for _ in range(ins)) + \
+        r2[rnd.randint(0, 8):m2 - rnd.randint(0, 8)]
+    c = list("".join(rnd.choice(alpha) for _ in range(rnd.randint(0, n_flank))) + core +
+             "".join(rnd.choice(alpha) for _ in range(rnd.randint(0, n_flank))))
+    for _ in range(int(len(c) * err)):
+        p = rnd.randrange(len(c))
+        op = rnd.random()
+        if op < 0.4:
+            c[p] = rnd.choice(alpha)
+        elif op < 0.7:
+            del c[p]
+        else:
+            c.insert(p, rnd.choice(alpha))
+    return "".join(c), r1, r2
+
+
+def test_locate_bp_shaped_problems_against_c_oracle(engine):
+    """Consensus contigs of a few hundred to ~2000 bases against +-20 bp breakpoint regions (mode d/r/t) and reference
+    windows against 500-base contig ends (mode i), default get parameters 1/3/3/2 (arg_parser.py:121)."""
+    rnd = random.Random(2026)
+    probs = []
+    for _ in range(40):
+        probs.append(_junction_problem(rnd, 300, rnd.randint(40, 400), rnd.randint(40, 400), rnd.choice([0, 0, 5, 60]), 0.03))
+    for _ in range(6):      # larger: 2 kb contig, ~1 kb regions
+        probs.append(_junction_problem(rnd, 600, rnd.randint(700, 1100), rnd.randint(700, 1100), rnd.choice([0, 30]), 0.04))
+    for _ in range(10):     # mode "i": the reference window plays the contig role, contig ends play the regions
+        probs.append(_junction_problem(rnd, 100, 500, 500, 0, 0.02))
+    for _ in range(8):      # unrelated -> None
+        probs.append(("".join(rnd.choice("ACGT") for _ in range(rnd.randint(50, 500))),
+                      "".join(rnd.choice("ACGT") for _ in range(rnd.randint(30, 200))),
+                      "".join(rnd.choice("ACGT") for _ in range(rnd.randint(30, 200)))))
+    for prm in ((1, 3, 3, 2, 10), (1, 2, 2, 2, 10)):
+        got = SW.sw_jump_batch(probs, *prm, engine=engine)
+        n_none = 0
+        for (c, r1, r2), g in zip(probs, got):
+            exp = O.sw_jump(c, r1, r2, *prm)
+            assert g == exp, (len(c), len(r1), len(r2), prm)
+            n_none += exp is None
+        assert 4 <= n_none < len(probs) // 2
+
+
+def test_edge_shapes(engine):
+    cases = [("A", "A", "A"), ("ACGT", "A", "T"), ("ACGTACGTACGTACGTACGTAAAACCCCGGGGTTTTACGT", "ACGTACGTACGTACGTACGT", "AAAACCCCGGGGTTTTACGT"),
+             ("N" * 30 + "ACGTTGCA" * 5, "N" * 30, "ACGTTGCA" * 5), ("acgt" * 10 + "ACGT" * 10, "acgt" * 10, "ACGT" * 10)]
+    for prm in ((1, 2, 2, 2, 10), (1, 1, 1, 1, 3)):
+        got = SW.sw_jump_batch(cases, *prm, engine=engine)
+        for (c, r1, r2), g in zip(cases, got):
+            assert g == O.sw_jump(c, r1, r2, *prm)
+    assert SW.sw_jump_batch([], engine=engine) == []
+    with pytest.raises(ValueError):
+        SW.sw_jump("", "A", "A", engine=engine)
