@@ -13,28 +13,31 @@ from . import _lib
 from .engine import Engine, default_engine
 
 
+_DASH = np.uint8(ord("-"))
+
+
+def _walk(seq_c: np.ndarray, seq_r: np.ndarray, i_end: int, j_end: int, ops: np.ndarray) -> Tuple[bytes, bytes]:
+    """Alignment rows of one traceback (reference smith_waterman.py:71-125), vectorised: operation k consumes a contig
+    base when its code is 1, 2 (or 4, the jump cell) and a region base when it is 1, 3 (or 4)."""
+    if len(ops) == 0:
+        return b"", b""
+    uses_c = (ops == 1) | (ops == 2) | (ops == 4)
+    uses_r = (ops == 1) | (ops == 3) | (ops == 4)
+    moves_c = (ops == 1) | (ops == 2)
+    moves_r = (ops == 1) | (ops == 3)
+    i = i_end - np.concatenate(([0], np.cumsum(moves_c[:-1])))
+    j = j_end - np.concatenate(([0], np.cumsum(moves_r[:-1])))
+    c = np.where(uses_c, seq_c[np.clip(i - 1, 0, len(seq_c) - 1)], _DASH)
+    g = np.where(uses_r, seq_r[np.clip(j - 1, 0, len(seq_r) - 1)], _DASH)
+    return c[::-1].tobytes(), g[::-1].tobytes()
+
+
 def _strings(contig: str, region1: str, region2: str, r, ops: np.ndarray) -> Tuple[str, str]:
-    c2, g2 = [], []
-    i, j = int(r["i2_end"]), int(r["j2_end"])
-    for p in ops[:int(r["n_ops2"])]:
-        if p == 1:
-            c2.append(contig[i - 1]); g2.append(region2[j - 1]); i -= 1; j -= 1
-        elif p == 2:
-            c2.append(contig[i - 1]); g2.append("-"); i -= 1
-        elif p == 3:
-            c2.append("-"); g2.append(region2[j - 1]); j -= 1
-        elif p == 4:
-            c2.append(contig[i - 1]); g2.append(region2[j - 1])
-    c1, g1 = [], []
-    i, j = int(r["i1_end"]), int(r["j1_end"])
-    for p in ops[int(r["n_ops2"]):int(r["n_ops2"]) + int(r["n_ops1"])]:
-        if p == 1:
-            c1.append(contig[i - 1]); g1.append(region1[j - 1]); i -= 1; j -= 1
-        elif p == 2:
-            c1.append(contig[i - 1]); g1.append("-"); i -= 1
-        elif p == 3:
-            c1.append("-"); g1.append(region1[j - 1]); j -= 1
-    return "".join(reversed(c1)) + " " + "".join(reversed(c2)), "".join(reversed(g1)) + " " + "".join(reversed(g2))
+    cb = np.frombuffer(contig.encode("latin-1"), dtype=np.uint8)
+    n2, n1 = int(r["n_ops2"]), int(r["n_ops1"])
+    c2, g2 = _walk(cb, np.frombuffer(region2.encode("latin-1"), dtype=np.uint8), int(r["i2_end"]), int(r["j2_end"]), ops[:n2])
+    c1, g1 = _walk(cb, np.frombuffer(region1.encode("latin-1"), dtype=np.uint8), int(r["i1_end"]), int(r["j1_end"]), ops[n2:n2 + n1])
+    return (c1 + b" " + c2).decode("latin-1"), (g1 + b" " + g2).decode("latin-1")
 
 
 def sw_jump_batch(problems: Sequence[Tuple[str, str, str]], match_score: int = 1, mismatch_penalty: int = 2,
