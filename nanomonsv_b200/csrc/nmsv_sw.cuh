@@ -197,7 +197,6 @@ sw_wavefront_kernel(const SwParams p)
     const uint32_t FLOOR0 = pack16(bias, bias);
     const uint32_t EF0 = pack16(bias - p.open, bias - p.open);          // E = F = -open
     constexpr bool kFixedGaps = (OPEN >= 0 && EXT >= 0);
-    const uint32_t NEG_OPEN = kFixedGaps ? (((uint32_t)(-OPEN) & 0xffffu) * 65537u) : p.neg_open2;            // H - open
     const uint32_t EXT_M_OPEN = kFixedGaps ? (((uint32_t)(EXT - OPEN) & 0xffffu) * 65537u) : p.ext_m_open2;   // H + ext - open
     const int ext = p.ext;
     const bool is_lane0 = (lane == 0);
@@ -232,7 +231,7 @@ sw_wavefront_kernel(const SwParams p)
         const int ntiles = (rows + 32 * R - 1) / (32 * R);
         const int total_steps = (ncols + 31 + 3) & ~3;   // multiple of 4: the step body is unrolled 4x (pad steps are inert)
         // steps the bias may run before the 16-bit lanes could overflow (host guarantees >= kChunk)
-        const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext : 0x7fffffff;
+        const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext - R - 4 : 0x7fffffff;
 
         // running best over tiles, per half: {score, col, row}
         int bs0 = 0, bc0 = 0, br0 = a_len - 1;
@@ -248,7 +247,7 @@ sw_wavefront_kernel(const SwParams p)
             const bool stage_lane = write_bnd && lane == 31;
 
             __syncwarp();
-            // ---- profile of this tile: prof[code][group][lane].{x,y,z,w} = (S_A | S_B << 16) + ext of row 4*group+w
+            // ---- profile of this tile: prof[code][group][lane].{x,y,z,w} = (S_A | S_B << 16) + 2*ext of row 4*group+w
             {
                 uint32_t* pw = reinterpret_cast<uint32_t*>(prof);
                 for (int k = 0; k < 4 * G; ++k) {
@@ -257,37 +256,45 @@ sw_wavefront_kernel(const SwParams p)
                     const int cb = (k < R && row < b_len) ? fetch_code(p.codes, task.b_base, row, b_rev, b_comp) : kRowPad;
 #pragma unroll
                     for (int b = 0; b < kNumCodes; ++b) {
-                        const uint32_t w = pack16(sub_score(ca, b, p.match, p.mismatch) + p.ext,
-                                                  sub_score(cb, b, p.match, p.mismatch) + p.ext);
+                        const uint32_t w = pack16(sub_score(ca, b, p.match, p.mismatch) + 2 * p.ext,
+                                                  sub_score(cb, b, p.match, p.mismatch) + 2 * p.ext);
                         pw[(((b * G) + (k >> 2)) * 32 + lane) * 4 + (k & 3)] = w;
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < (2 * kRing) / 32; ++u) rring[u * 32 + lane] = (uint8_t)kPadCode;
-                if (lane == 0) bconst[0] = make_uint2((uint32_t)(ext * 65537), (uint32_t)(ext * 65537));
+                if (lane == 0) {      // bias change from (step t-1, row R-1 / R) of the lane above to (step t, row -1 / 0)
+                    const uint32_t lift = (uint32_t)(-((R - 1) * ext * 65537));
+                    bconst[0] = make_uint2(lift, lift);
+                }
             }
 
             // H of the previous column ping-pongs between HA and HB over a 2-step unrolled body, so that no
             // register moves are needed to keep Hdiag alive while the new column is written.
             uint32_t HA[R], HB[R], E[R];
 #pragma unroll
-            for (int k = 0; k < R; ++k) { HA[k] = FLOOR0; HB[k] = FLOOR0; E[k] = EF0; }
+            for (int k = 0; k < R; ++k) {       // zero state with the bias of "after step -1": row k carries k*ext
+                HA[k] = FLOOR0 + (uint32_t)k * p.ext2; HB[k] = HA[k]; E[k] = EF0 + (uint32_t)(k + 1) * p.ext2;
+            }
             // later tiles start their running maximum at (best of the earlier tiles - 1), per half
             uint32_t bestprev = FLOOR0 + pack16(bs0 > 0 ? bs0 - 1 : 0, bs1 > 0 ? bs1 - 1 : 0);
-            uint32_t flb = FLOOR0 + p.ext2;     // floor of step t is flb + t*ext2 = FLOOR0 + (t - tbase)*ext2, tbase = -1
+            uint32_t flb = FLOOR0 + p.ext2;     // floor of row k at step t is flb + (t+k)*ext2 = FLOOR0 + (t - tbase + k)*ext2
             int col_lo = 0, row_lo = 0, col_hi = 0, row_hi = 0;   // only meaningful once best rose above the floor
-            uint32_t h_last = FLOOR0, f_out = EF0, diag = FLOOR0;
-            int tbase = -1;          // beta_t = (t - tbase) * ext ; state "after step -1" carries beta = 0
+            uint32_t h_last = FLOOR0 + (uint32_t)(R - 1) * p.ext2, f_out = EF0 + (uint32_t)R * p.ext2, diag = FLOOR0 - p.ext2;
+            int tbase = -1;          // bias of row k at step t = (t - tbase + k) * ext ; "after step -1" row 0 carries 0
             // TMA staging applies to forward reads that start on a 16-byte boundary; whether a given chunk was
             // prefetched is a pure function of t0 (a mutable flag would cost the compiler its uniformity analysis)
             const bool tma_task = !c_rev && ((task.c_base & 15ull) == 0);
 
             // Filter threshold for TWO consecutive columns at once: no row of either column exceeds the running maximum
             // if no sampled row comes within open + 2*ext of it; the older column is compared one ext too strictly.
-            const uint32_t MARGIN2 = (uint32_t)((p.open + 3 * ext) * 65537);
+#ifndef NMSV_SAMPLE_STRIDE
+#define NMSV_SAMPLE_STRIDE 4
+#endif
+            const uint32_t MARGIN2 = (uint32_t)((p.open + (NMSV_SAMPLE_STRIDE - 1) * ext) * 65537);
             // One column. tq = t - U is a multiple of 4, so every ring index of step t is a base computed once per four
             // steps plus the compile-time constant U (no per-step uniform-datapath arithmetic).
-            auto column = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const uint32_t fl, const char* bq,
+            auto column = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const uint32_t (&FL)[R + 3], const char* bq,
                               const uint8_t* rq, uint2* sq, const int U) {
                 const uint32_t sh = __shfl_up_sync(kFull, h_last, 1);
                 const uint32_t sf = __shfl_up_sync(kFull, f_out, 1);
@@ -307,10 +314,9 @@ sw_wavefront_kernel(const SwParams p)
 #pragma unroll
                 for (int k = 0; k < R; ++k) {
                     const uint32_t x = __viaddmax_s16x2(k == 0 ? diag : Hs[k - 1], S[k], E[k]);  // max(Hdiag + S, E)
-                    const uint32_t h = __vimax3_s16x2(x, fl, F);                                 // H = max(x, F, 0)
-                    const uint32_t fd = add_halves(F, -ext);                                     // F - ext (FMA pipe)
+                    const uint32_t h = __vimax3_s16x2(x, FL[U + k], F);                          // H = max(x, F, 0)
                     E[k] = __viaddmax_s16x2(h, EXT_M_OPEN, E[k]);                                // E' = max(H-open, E-ext)
-                    F = __viaddmax_s16x2(h, NEG_OPEN, fd);                                       // F' for the next row
+                    F = __viaddmax_s16x2(h, EXT_M_OPEN, F);                                      // F' = max(H-open, F-ext)
                     Hd[k] = h;
                 }
                 diag = hin;
@@ -322,42 +328,49 @@ sw_wavefront_kernel(const SwParams p)
             // Rows k and k' <= k of one column satisfy H[k] >= H[k'] - open - (k-k'-1)*ext (through F), so if no row
             // of {R-1, R-5, ...} comes within the margin of the running maximum no row of the strip exceeds it:
             // 1 DPX per 8 rows and column instead of 1 per 2 rows in the common case.
+            auto negk = [&](const int k) -> uint32_t {      // (-k*ext, -k*ext): removes the row part of the bias
+                return kFixedGaps ? (((uint32_t)(-k * EXT)) & 0xffffu) * 65537u : (((uint32_t)(-k * ext)) & 0xffffu) * 65537u;
+            };
             auto track = [&](const uint32_t (&Ha)[R], const uint32_t (&Hb)[R], const int t) {
-                const uint32_t bp2 = add_halves(bestprev, 2 * ext);      // running maximum at the newer column's bias
+                const uint32_t bp2 = add_halves(bestprev, 2 * ext);      // running maximum at the newer step's row-0 bias
                 const uint32_t thr = bp2 - MARGIN2;                       // floors >= open + 2*ext: no borrow
                 uint32_t q = thr;
 #pragma unroll
-                for (int k = R - 1; k >= 0; k -= 8) {
-                    q = __vimax3_s16x2(q, Ha[k], Ha[k >= 4 ? k - 4 : k]);
-                    q = __vimax3_s16x2(q, Hb[k], Hb[k >= 4 ? k - 4 : k]);
+                for (int k = R - 1; k >= 0; k -= NMSV_SAMPLE_STRIDE) {
+                    q = __viaddmax_s16x2(Ha[k], negk(k), q);
+                    q = __viaddmax_s16x2(Hb[k], negk(k), q);
                 }
                 uint32_t best = bp2;
                 if (q != thr) {
                     // rare: some row may exceed this lane's running maximum. One prefix-maximum pass per column: VIMNMX
                     // with predicate outputs tells per half whether H[k] strictly beats everything before it; the
-                    // last such row is the first row holding the column maximum (parasail: smallest row).
+                    // last such row is the first row holding the column maximum (parasail: smallest row). The running
+                    // value follows the row bias (+ext per row) and is brought back to row 0 afterwards.
                     best = add_halves(bestprev, ext);
                     int rl = -1, rh = -1;
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         bool keep_hi, keep_lo;                       // keep_* = (best >= H[k]) in that half
+                        if (k > 0) best = add_halves(best, ext);
                         best = __vibmax_s16x2(best, Ha[k], &keep_hi, &keep_lo);
                         if (!keep_lo) rl = k;
                         if (!keep_hi) rh = k;
                     }
                     if (rl >= 0) { col_lo = t - lane; row_lo = row0 + rl; }
                     if (rh >= 0) { col_hi = t - lane; row_hi = row0 + rh; }
-                    best = add_halves(best, ext);
+                    best = add_halves(best, ext - (R - 1) * ext);      // back to row 0, then on to the newer step
                     rl = -1; rh = -1;
 #pragma unroll
                     for (int k = 0; k < R; ++k) {
                         bool keep_hi, keep_lo;
+                        if (k > 0) best = add_halves(best, ext);
                         best = __vibmax_s16x2(best, Hb[k], &keep_hi, &keep_lo);
                         if (!keep_lo) rl = k;
                         if (!keep_hi) rh = k;
                     }
                     if (rl >= 0) { col_lo = t + 1 - lane; row_lo = row0 + rl; }
                     if (rh >= 0) { col_hi = t + 1 - lane; row_hi = row0 + rh; }
+                    best = add_halves(best, -(R - 1) * ext);
                 }
                 bestprev = best;
             };
@@ -385,9 +398,10 @@ sw_wavefront_kernel(const SwParams p)
                             c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
                         if (tile > 0) bv = __ldcg(bnd_in + col);
                     }
-                    // lane 0 consumes entry `col` at step col: store it with that step's bias beta_col
+                    // lane 0 consumes entry `col` at step col as (H of row -1 for the next step's diagonal, F entering
+                    // row 0): biases (col - 1 - tbase) * ext and (col - tbase) * ext
                     const uint32_t bb = (uint32_t)((col - tbase) * ext) * 65537u;
-                    bv.x += bb; bv.y += bb;
+                    bv.x += bb - p.ext2; bv.y += bb;
                     if (!prefetched) {
                         rring[col & (kRing - 1)] = c;
                         rring[(col & (kRing - 1)) + kRing] = c;
@@ -422,15 +436,18 @@ sw_wavefront_kernel(const SwParams p)
                 for (int g0 = t0; g0 < t1; g0 += 32) {
                     const int g1 = (g0 + 32 < t1) ? g0 + 32 : t1;     // g1 - g0 is even (total_steps is even)
                     for (int t = g0; t < g1; t += 4) {        // g0, g1 and total_steps are multiples of 4
-                        const uint32_t fl = flb + (uint32_t)t * p.ext2;        // floor of step t: warp-uniform
+                        uint32_t FL[R + 3];      // floors of (step t+u, row k) = FL[u + k]: warp-uniform sliding window
+                        FL[0] = flb + (uint32_t)t * p.ext2;
+#pragma unroll
+                        for (int i = 1; i < R + 3; ++i) FL[i] = add_halves(FL[i - 1], ext);     // IMAD chain, FMA pipe
                         const char* bq = bsrc + (uint32_t)(t & (kChunk - 1)) * bstride;
                         const uint8_t* rq = rlane + (t & (kRing - 1));
                         uint2* sq = bstage + (t & 31);
-                        column(HA, HB, fl, bq, rq, sq, 0);
-                        column(HB, HA, fl + p.ext2, bq, rq, sq, 1);
+                        column(HA, HB, FL, bq, rq, sq, 0);
+                        column(HB, HA, FL, bq, rq, sq, 1);
                         track(HB, HA, t);
-                        column(HA, HB, fl + 2 * p.ext2, bq, rq, sq, 2);
-                        column(HB, HA, fl + 3 * p.ext2, bq, rq, sq, 3);
+                        column(HA, HB, FL, bq, rq, sq, 2);
+                        column(HB, HA, FL, bq, rq, sq, 3);
                         track(HB, HA, t + 2);
                     }
                     // ---- event filter: only a cell that reaches the final maximum of the whole alignment matters, and
@@ -454,8 +471,8 @@ sw_wavefront_kernel(const SwParams p)
                         const int col = tp - 31;
                         if (tp < g1 && col >= 0 && col < ncols) {
                             uint2 v = bstage[lane];
-                            const uint32_t bb = (uint32_t)((tp - tbase) * ext) * 65537u;
-                            v.x -= bb; v.y -= bb;
+                            const uint32_t bb = (uint32_t)((tp - tbase + R - 1) * ext) * 65537u;   // row R-1 at step tp
+                            v.x -= bb; v.y -= bb + p.ext2;
                             __stcg(bnd_out + col, v);
                         }
                         __syncwarp();
