@@ -317,7 +317,9 @@ struct DevBuf {
 // ------------------------------------------------------------------------------------------------------------------
 struct Sel { int32_t score, erow, ecol, strand; };   // chosen strand of one (read, slot)
 
-enum : uint32_t { kCntFwdQueue = 0, kCntRevQueue = 8, kCntRevTasks = 16, kCntRecords = 17, kCntStatus = 18, kCntTotal = 32 };
+// per strip class (index = position in the plan's class list, at most 8): forward queue head, begin queue head and
+// begin queue reservation count
+enum : uint32_t { kCntFwdQueue = 0, kCntRevQueue = 8, kCntRecords = 17, kCntStatus = 18, kCntRevReserve = 24, kCntTotal = 32 };
 enum : uint8_t { kReadCandidate = 1, kReadSupporting = 2 };
 
 __device__ __forceinline__ int alias_of(const nmsv_sv& sv, int s)
@@ -331,7 +333,7 @@ __device__ __forceinline__ int alias_of(const nmsv_sv& sv, int s)
 __global__ void plan_fwd_kernel(const nmsv_sv* __restrict__ svs, const nmsv_read* __restrict__ reads,
                                 const uint32_t* __restrict__ order, const uint64_t* __restrict__ offsets,
                                 const uint32_t* __restrict__ lens, const uint8_t* __restrict__ seq_class,
-                                uint32_t n_reads, SwTask* __restrict__ tasks)
+                                uint32_t n_reads, SwTask* __restrict__ tasks, uint32_t* __restrict__ group_remaining)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_reads * 4u) return;
@@ -356,6 +358,7 @@ __global__ void plan_fwd_kernel(const nmsv_sv* __restrict__ svs, const nmsv_read
         t.c_base = offsets[rd.seq];
         t.ncols = lens[rd.seq];
         t.rclass = (uint32_t)seq_class[tm];   // strip height R itself
+        if (t.ncols) atomicAdd(&group_remaining[r], 1u);      // zeroed before the launch
     }
     tasks[i] = t;
 }
@@ -364,9 +367,13 @@ struct DecideParams {
     const nmsv_sv* svs; const nmsv_read* reads; const uint64_t* offsets; const uint32_t* lens;
     const uint8_t* seq_class; uint32_t n_reads;
     const SwResult* fwd; Sel* sel; uint8_t* read_flags;
-    SwTask* rev_tasks; uint32_t* counters;
+    // begin-pass queues: one region of rev_capacity entries per strip class in use (region_of_r: R -> region index)
+    SwTask* rev_tasks; uint32_t* rev_ready; uint32_t rev_capacity; uint32_t* counters;
+    uint8_t region_of_r[kMaxR + 1];
     int match, open, ext;
 };
+
+namespace nmsv { struct GroupHook { DecideParams d; }; }
 
 __device__ __forceinline__ bool slot_present(const nmsv_sv& sv, int s)
 {
@@ -405,15 +412,22 @@ __device__ __forceinline__ void emit_rev_task(const DecideParams& p, uint32_t ou
     t.flags |= kCRev;
     t.ncols = window_cols(sl.erow + 1, sl.score, sl.ecol, p.match, p.open, p.ext);
     t.out = out;
+    t.best0 = (uint32_t)sl.score;       // only the cells that reach the forward score can be the begin cell
     t.rclass = (uint32_t)p.seq_class[tm];
-    const uint32_t idx = atomicAdd(&p.counters[kCntRevTasks], 1u);
-    p.rev_tasks[idx] = t;
+    // publish: body, fence, ready flag (the forward launch of this class may be draining the queue right now)
+    const uint32_t region = p.region_of_r[t.rclass];
+    const uint32_t idx = atomicAdd(&p.counters[kCntRevReserve + region], 1u);
+    const size_t at = (size_t)region * p.rev_capacity + idx;
+    p.rev_tasks[at] = t;
+    __threadfence();
+    atomicExch(&p.rev_ready[at], 1u);
 }
 
-__global__ void decide_kernel(const DecideParams p)
+// The decision for one read once all its forward alignments are known. Runs either as a thread of decide_kernel or,
+// on the fused path, on lane 0 of the warp that finished the read's last forward task (results of the other tasks come
+// from other SMs: L2 loads).
+__device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r)
 {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.n_reads) return;
     const nmsv_read rd = p.reads[r];
     const nmsv_sv sv = p.svs[rd.sv];
     Sel sl[4];
@@ -423,7 +437,10 @@ __global__ void decide_kernel(const DecideParams p)
         present[s] = slot_present(sv, s);
         Sel x = {0, 0, 0, 0};
         if (present[s]) {
-            const SwResult f = p.fwd[r * 4u + (uint32_t)alias_of(sv, s)];
+            const int2* fp = reinterpret_cast<const int2*>(p.fwd + r * 4u + (uint32_t)alias_of(sv, s));
+            const int2 f0 = __ldcg(fp), f1 = __ldcg(fp + 1), f2 = __ldcg(fp + 2);
+            SwResult f;
+            f.score[0] = f0.x; f.score[1] = f0.y; f.row[0] = f1.x; f.row[1] = f1.y; f.col[0] = f2.x; f.col[1] = f2.y;
             if (f.score[0] > f.score[1]) { x.score = f.score[0]; x.erow = f.row[0]; x.ecol = f.col[0]; x.strand = 1; }
             else { x.score = f.score[1]; x.erow = f.row[1]; x.ecol = f.col[1]; x.strand = -1; }   // ties -> '-'
         }
@@ -460,6 +477,14 @@ __global__ void decide_kernel(const DecideParams p)
             emit_rev_task(p, r * 4u + (uint32_t)s, sv.tmpl[s], sv.tmpl_rc[s], rd.seq, sl[s]);
 }
 
+__global__ void decide_kernel(const DecideParams p)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < p.n_reads) decide_read(p, r);
+}
+
+__device__ void nmsv::sw_group_done(const GroupHook* hook, uint32_t out) { decide_read(hook->d, out >> 2); }
+
 __device__ __forceinline__ nmsv_aln make_aln(const Sel& sl, int m, int brow, int bcol)
 {
     nmsv_aln a;
@@ -495,7 +520,8 @@ __global__ void final_kernel(const FinalParams p)
             int brow = 0, bcol = 0;
             if (cand && sl.score > 0) {
                 const SwResult rv = p.rev[r * 4u + (uint32_t)alias_of(sv, s)];
-                if (rv.score[0] != sl.score) atomicAdd(&p.counters[kCntStatus], 1u);   // window bound violated
+                if (rv.score[0] != sl.score || rv.col[0] == 0x7fffffff)                // window bound violated: no cell
+                    atomicAdd(&p.counters[kCntStatus], 1u);                            // of the window reached the score
                 brow = sl.erow - rv.row[0];
                 bcol = sl.ecol - rv.col[0];
             }
@@ -532,7 +558,9 @@ struct PairParams {
     const uint64_t* offsets; const uint32_t* lens; const uint8_t* seq_class;
     const uint32_t* tmpl_idx; const uint32_t* rc_idx; const uint32_t* read_idx; uint32_t n_pairs;
     int both_strands;
-    const SwResult* fwd; Sel* sel; SwTask* rev_tasks; const SwResult* rev; uint32_t* counters;
+    const SwResult* fwd; Sel* sel; SwTask* rev_tasks; uint32_t* rev_ready; uint32_t rev_capacity;
+    uint8_t region_of_r[kMaxR + 1];
+    const SwResult* rev; uint32_t* counters;
     nmsv_ssw_result* out_ssw; nmsv_aln* out_aln; int want_begin;
     int match, open, ext;
 };
@@ -572,6 +600,8 @@ __global__ void pair_decide_kernel(const PairParams p)
     if (!p.want_begin || x.score <= 0) return;
     DecideParams d;
     d.offsets = p.offsets; d.lens = p.lens; d.seq_class = p.seq_class; d.rev_tasks = p.rev_tasks; d.counters = p.counters;
+    d.rev_ready = p.rev_ready; d.rev_capacity = p.rev_capacity;
+    for (int q = 0; q <= kMaxR; ++q) d.region_of_r[q] = p.region_of_r[q];
     d.match = p.match; d.open = p.open; d.ext = p.ext;
     emit_rev_task(d, i, p.tmpl_idx[i], p.rc_idx ? p.rc_idx[i] : NMSV_NONE, p.read_idx[i], x);
 }
@@ -584,7 +614,7 @@ __global__ void pair_final_kernel(const PairParams p)
     int brow = 0, bcol = 0;
     if (p.want_begin && x.score > 0) {
         const SwResult rv = p.rev[i];
-        if (rv.score[0] != x.score) atomicAdd(&p.counters[kCntStatus], 1u);
+        if (rv.score[0] != x.score || rv.col[0] == 0x7fffffff) atomicAdd(&p.counters[kCntStatus], 1u);
         brow = x.erow - rv.row[0];
         bcol = x.ecol - rv.col[0];
     }
@@ -633,9 +663,9 @@ static int check_template(nmsv_ctx* ctx, uint32_t idx, const uint32_t* lens, uin
     if (idx >= n_seqs) return set_err(ctx, NMSV_E_INVALID, "%s index %u out of range (n_seqs %u)", what, idx, n_seqs);
     if (lens[idx] == 0) return set_err(ctx, NMSV_E_INVALID, "%s %u is empty", what, idx);
     // parasail: NULL when any H exceeds INT16_MAX - max(matrix) - 1 ; H <= match * rows
-    // plus the kernel's bias head-room: a = open+ext and one chunk of per-step ext increments
-    if ((uint64_t)sc->match * lens[idx] + (uint64_t)(sc->gap_open + sc->gap_extend) +
-            (uint64_t)(kChunk + 2) * sc->gap_extend > 32767u - (uint32_t)sc->match - 1u)
+    // plus the kernel's bias head-room (nmsv_sw.cuh: sw_headroom)
+    if ((uint64_t)sc->match * lens[idx] + (uint64_t)sw_headroom(sc->gap_open, sc->gap_extend) >
+            32767u - (uint32_t)sc->match - 1u)
         return set_err(ctx, NMSV_E_RANGE, "%s %u of length %u could score beyond the 16-bit range (parasail.ssw would return None)",
                        what, idx, lens[idx]);
     return NMSV_OK;
@@ -679,7 +709,9 @@ struct nmsv_plan {
     uint32_t n_seqs = 0, n_svs = 0, n_reads = 0;
     nmsv_scoring sc{};
     SeqTables st;
-    DevBuf svs, reads, order, tasks, fwd, rev_tasks, rev, sel, alns, flags, supporting, records, counters, bnd;
+    DevBuf svs, reads, order, tasks, fwd, rev_tasks, rev_ready, group_remaining, hook, rev, sel, alns, flags, supporting,
+           records, counters, bnd;
+    bool fused_begin = true;      // begin tasks are drained by the forward launches (NMSV_FUSED_BEGIN=0: separate launches only)
     uint32_t bnd_stride = 1;
     std::vector<int> classes;          // indices into kClassR that occur in this batch
     std::vector<int32_t> checked;
@@ -815,7 +847,16 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
     const uint64_t nslots = (uint64_t)n_reads * 4;
     CUDA_TRY(ctx, pl->tasks.alloc(sizeof(SwTask) * nslots, s));
     CUDA_TRY(ctx, pl->fwd.alloc(sizeof(SwResult) * nslots, s));
-    CUDA_TRY(ctx, pl->rev_tasks.alloc(sizeof(SwTask) * nslots, s));
+    const uint64_t n_regions = std::max<size_t>(1, pl->classes.size());
+    if (n_regions > 8) return set_err(ctx, NMSV_E_INTERNAL, "more than 8 strip classes in one plan");
+    CUDA_TRY(ctx, pl->rev_tasks.alloc(sizeof(SwTask) * nslots * n_regions, s));
+    CUDA_TRY(ctx, pl->rev_ready.alloc(sizeof(uint32_t) * nslots * n_regions, s));
+    CUDA_TRY(ctx, pl->group_remaining.alloc(sizeof(uint32_t) * (uint64_t)n_reads, s));
+    CUDA_TRY(ctx, pl->hook.alloc(sizeof(GroupHook), s));
+    {
+        const char* e = getenv("NMSV_FUSED_BEGIN");
+        pl->fused_begin = !(e && e[0] == '0');
+    }
     CUDA_TRY(ctx, pl->rev.alloc(sizeof(SwResult) * nslots, s));
     CUDA_TRY(ctx, pl->sel.alloc(sizeof(Sel) * nslots, s));
     CUDA_TRY(ctx, pl->alns.alloc(sizeof(nmsv_aln) * nslots, s));
@@ -826,10 +867,11 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
     pl->bnd_stride = max_cols_multi ? max_cols_multi : 1;
     const uint64_t bnd_bytes = max_cols_multi ? (uint64_t)max_grid_warps(ctx) * pl->bnd_stride * sizeof(uint2) : 16;
     CUDA_TRY(ctx, pl->bnd.alloc(bnd_bytes, s));
-    stt.workspace_bytes = pl->tasks.bytes + pl->fwd.bytes + pl->rev_tasks.bytes + pl->rev.bytes + pl->sel.bytes +
+    stt.workspace_bytes = pl->tasks.bytes + pl->fwd.bytes + pl->rev_tasks.bytes + pl->rev_ready.bytes +
+                          pl->group_remaining.bytes + pl->rev.bytes + pl->sel.bytes +
                           pl->alns.bytes + pl->flags.bytes + pl->supporting.bytes + pl->records.bytes + pl->bnd.bytes;
     stt.n_classes = (uint32_t)pl->classes.size();
-    stt.kernel_launches = 3 + 2 * stt.n_classes;
+    stt.kernel_launches = (pl->fused_begin ? 2u : 3u) + 2 * stt.n_classes;
     // the caller's host buffers may be reused as soon as we return
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     guard.p = nullptr;
@@ -855,36 +897,63 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     auto note = [&](uint32_t phase, uint32_t rclass) { pl->launch_phase.push_back(phase); pl->launch_rclass.push_back(rclass); };
     mark(pl, ev, s);
 
+    CUDA_TRY(ctx, cudaMemsetAsync(pl->group_remaining.p, 0, pl->group_remaining.bytes, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(pl->rev_ready.p, 0, pl->rev_ready.bytes, s));
     plan_fwd_kernel<<<(nslots + tpb - 1) / tpb, tpb, 0, s>>>(pl->svs.as<nmsv_sv>(), pl->reads.as<nmsv_read>(),
         pl->order.as<uint32_t>(), pl->st.offsets.as<uint64_t>(), pl->st.lens.as<uint32_t>(), pl->st.seq_class.as<uint8_t>(),
-        n_reads, pl->tasks.as<SwTask>());
+        n_reads, pl->tasks.as<SwTask>(), pl->group_remaining.as<uint32_t>());
     note(kPhasePlan, 0); mark(pl, ev, s);
 
+    GroupHook hk;
+    memset(&hk, 0, sizeof(hk));
+    DecideParams& dp = hk.d;
+    dp.svs = pl->svs.as<nmsv_sv>(); dp.reads = pl->reads.as<nmsv_read>(); dp.offsets = pl->st.offsets.as<uint64_t>();
+    dp.lens = pl->st.lens.as<uint32_t>(); dp.seq_class = pl->st.seq_class.as<uint8_t>(); dp.n_reads = n_reads;
+    dp.fwd = pl->fwd.as<SwResult>(); dp.sel = pl->sel.as<Sel>(); dp.read_flags = pl->flags.as<uint8_t>();
+    dp.rev_tasks = pl->rev_tasks.as<SwTask>(); dp.rev_ready = pl->rev_ready.as<uint32_t>(); dp.rev_capacity = nslots;
+    dp.counters = pl->counters.as<uint32_t>();
+    for (size_t i = 0; i < pl->classes.size(); ++i) dp.region_of_r[kClassR[pl->classes[i]]] = (uint8_t)i;
+    dp.match = pl->sc.match; dp.open = pl->sc.gap_open; dp.ext = pl->sc.gap_extend;
+    if (pl->fused_begin) {      // the hook lives in device memory; the host copy is pageable, so this copy is staged before returning
+        CUDA_TRY(ctx, cudaMemcpyAsync(pl->hook.p, &hk, sizeof(hk), cudaMemcpyHostToDevice, s));
+    }
+
     SwParams sp;
+    memset(&sp, 0, sizeof(sp));
     sp.codes = pl->st.codes.as<uint8_t>();
     sp.bnd = pl->bnd.as<uint2>(); sp.bnd_stride = pl->bnd_stride;
     sp.match = pl->sc.match; sp.mismatch = pl->sc.mismatch; sp.open = pl->sc.gap_open; sp.ext = pl->sc.gap_extend;
     fill_packed(sp);
 
+    // forward launches, one per strip class. Fused path: the warp that completes the last forward task of a read decides
+    // it and queues its begin tasks; the launch of the tasks' class drains that queue alongside its forward tasks.
     sp.tasks = pl->tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = nslots; sp.results = pl->fwd.as<SwResult>();
     for (size_t i = 0; i < pl->classes.size(); ++i) {
         sp.queue_head = pl->counters.as<uint32_t>() + kCntFwdQueue + i;
+        if (pl->fused_begin) {
+            sp.hook = pl->hook.as<GroupHook>(); sp.group_remaining = pl->group_remaining.as<uint32_t>();
+            sp.dyn_tasks = dp.rev_tasks + i * (size_t)nslots; sp.dyn_ready = dp.rev_ready + i * (size_t)nslots;
+            sp.dyn_head = pl->counters.as<uint32_t>() + kCntRevQueue + i;
+            sp.dyn_reserve = pl->counters.as<uint32_t>() + kCntRevReserve + i;
+            sp.dyn_results = pl->rev.as<SwResult>();
+        }
         launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
         note(kPhaseFwd, (uint32_t)kClassR[pl->classes[i]]); mark(pl, ev, s);
     }
+    sp.hook = nullptr; sp.group_remaining = nullptr;
+    sp.dyn_tasks = nullptr; sp.dyn_ready = nullptr; sp.dyn_head = nullptr; sp.dyn_reserve = nullptr; sp.dyn_results = nullptr;
 
-    DecideParams dp;
-    dp.svs = pl->svs.as<nmsv_sv>(); dp.reads = pl->reads.as<nmsv_read>(); dp.offsets = pl->st.offsets.as<uint64_t>();
-    dp.lens = pl->st.lens.as<uint32_t>(); dp.seq_class = pl->st.seq_class.as<uint8_t>(); dp.n_reads = n_reads;
-    dp.fwd = pl->fwd.as<SwResult>(); dp.sel = pl->sel.as<Sel>(); dp.read_flags = pl->flags.as<uint8_t>();
-    dp.rev_tasks = pl->rev_tasks.as<SwTask>(); dp.counters = pl->counters.as<uint32_t>();
-    dp.match = pl->sc.match; dp.open = pl->sc.gap_open; dp.ext = pl->sc.gap_extend;
-    decide_kernel<<<(n_reads + tpb - 1) / tpb, tpb, 0, s>>>(dp);
-    note(kPhaseDecide, 0); mark(pl, ev, s);
+    if (!pl->fused_begin) {
+        decide_kernel<<<(n_reads + tpb - 1) / tpb, tpb, 0, s>>>(dp);
+        note(kPhaseDecide, 0); mark(pl, ev, s);
+    }
 
-    sp.tasks = pl->rev_tasks.as<SwTask>(); sp.n_tasks_dev = pl->counters.as<uint32_t>() + kCntRevTasks; sp.n_tasks = 0;
-    sp.results = pl->rev.as<SwResult>();
+    // begin launches over what is left in each class's queue (fused path: the tasks queued after their class's forward
+    // launch had run dry or finished; otherwise all of them)
+    sp.results = pl->rev.as<SwResult>(); sp.n_tasks = 0;
     for (size_t i = 0; i < pl->classes.size(); ++i) {
+        sp.tasks = dp.rev_tasks + i * (size_t)nslots;
+        sp.n_tasks_dev = pl->counters.as<uint32_t>() + kCntRevReserve + i;
         sp.queue_head = pl->counters.as<uint32_t>() + kCntRevQueue + i;
         launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
         note(kPhaseRev, (uint32_t)kClassR[pl->classes[i]]); mark(pl, ev, s);
@@ -953,7 +1022,8 @@ extern "C" int nmsv_plan_download(nmsv_plan* pl, int32_t* checked, int32_t* supp
     if (supporting && pl->n_svs)
         CUDA_TRY(ctx, cudaMemcpyAsync(supporting, pl->supporting.p, sizeof(int32_t) * pl->n_svs, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    pl->stats.rev_tasks = cnt[kCntRevTasks];
+    pl->stats.rev_tasks = 0;
+    for (uint32_t i = 0; i < 8; ++i) pl->stats.rev_tasks += cnt[kCntRevReserve + i];
     pl->stats.d2h_bytes = sizeof(cnt) + sizeof(int32_t) * (uint64_t)pl->n_svs;
     if (cnt[kCntStatus])
         return set_err(ctx, NMSV_E_INTERNAL, "%u begin-pass windows did not reproduce their forward score", cnt[kCntStatus]);
@@ -1053,7 +1123,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     cudaStream_t s = ctx->stream;
     rc = upload_seq_tables(ctx, st, codes, n_codes, offsets, lens, n_seqs);
     if (rc) return rc;
-    DevBuf d_t, d_rc, d_r, tasks, fwd, rev_tasks, rev, sel, counters, bnd, d_out;
+    DevBuf d_t, d_rc, d_r, tasks, fwd, rev_tasks, rev_ready, rev, sel, counters, bnd, d_out;
     CUDA_TRY(ctx, d_t.alloc(4ull * n_pairs, s));
     CUDA_TRY(ctx, d_r.alloc(4ull * n_pairs, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_t.p, tmpl_idx, 4ull * n_pairs, cudaMemcpyHostToDevice, s));
@@ -1064,7 +1134,10 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     }
     CUDA_TRY(ctx, tasks.alloc(sizeof(SwTask) * (uint64_t)n_pairs, s));
     CUDA_TRY(ctx, fwd.alloc(sizeof(SwResult) * (uint64_t)n_pairs, s));
-    CUDA_TRY(ctx, rev_tasks.alloc(sizeof(SwTask) * (uint64_t)n_pairs, s));
+    const uint64_t n_regions = want_begin ? std::max<size_t>(1, classes.size()) : 1;
+    const uint64_t rev_cap = want_begin ? n_pairs : 1;
+    CUDA_TRY(ctx, rev_tasks.alloc(sizeof(SwTask) * rev_cap * n_regions, s));
+    CUDA_TRY(ctx, rev_ready.alloc(sizeof(uint32_t) * rev_cap * n_regions, s));
     CUDA_TRY(ctx, rev.alloc(sizeof(SwResult) * (uint64_t)n_pairs, s));
     CUDA_TRY(ctx, sel.alloc(sizeof(Sel) * (uint64_t)n_pairs, s));
     CUDA_TRY(ctx, counters.alloc(sizeof(uint32_t) * kCntTotal, s));
@@ -1079,6 +1152,9 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     pp.tmpl_idx = d_t.as<uint32_t>(); pp.rc_idx = rc_idx ? d_rc.as<uint32_t>() : nullptr; pp.read_idx = d_r.as<uint32_t>();
     pp.n_pairs = n_pairs; pp.both_strands = both_strands;
     pp.fwd = fwd.as<SwResult>(); pp.sel = sel.as<Sel>(); pp.rev_tasks = rev_tasks.as<SwTask>(); pp.rev = rev.as<SwResult>();
+    pp.rev_ready = rev_ready.as<uint32_t>(); pp.rev_capacity = (uint32_t)rev_cap;
+    memset(pp.region_of_r, 0, sizeof(pp.region_of_r));
+    for (size_t i = 0; i < classes.size(); ++i) pp.region_of_r[kClassR[classes[i]]] = (uint8_t)i;
     pp.counters = counters.as<uint32_t>();
     pp.out_ssw = out_ssw ? d_out.as<nmsv_ssw_result>() : nullptr;
     pp.out_aln = out_ssw ? nullptr : d_out.as<nmsv_aln>();
@@ -1088,6 +1164,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     const int nb = (int)((n_pairs + tpb - 1) / tpb);
     pair_plan_kernel<<<nb, tpb, 0, s>>>(pp, tasks.as<SwTask>());
     SwParams sp;
+    memset(&sp, 0, sizeof(sp));
     sp.codes = st.codes.as<uint8_t>(); sp.bnd = bnd.as<uint2>(); sp.bnd_stride = stride;
     sp.match = sc->match; sp.mismatch = sc->mismatch; sp.open = sc->gap_open; sp.ext = sc->gap_extend;
     fill_packed(sp);
@@ -1098,9 +1175,10 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     }
     pair_decide_kernel<<<nb, tpb, 0, s>>>(pp);
     if (want_begin) {
-        sp.tasks = rev_tasks.as<SwTask>(); sp.n_tasks_dev = counters.as<uint32_t>() + kCntRevTasks; sp.n_tasks = 0;
-        sp.results = rev.as<SwResult>();
+        sp.n_tasks = 0; sp.results = rev.as<SwResult>();
         for (size_t i = 0; i < classes.size(); ++i) {
+            sp.tasks = rev_tasks.as<SwTask>() + i * rev_cap;
+            sp.n_tasks_dev = counters.as<uint32_t>() + kCntRevReserve + i;
             sp.queue_head = counters.as<uint32_t>() + kCntRevQueue + i;
             launch_class_idx(classes[i], sp, grid_for(ctx, classes[i]), s);
         }

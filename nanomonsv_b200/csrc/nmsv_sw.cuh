@@ -14,10 +14,17 @@
 //     free) so the inner loop has no compares; the read is staged through a shared-memory ring.
 //   * templates longer than one tile run tile after tile; the H/F row between two tiles goes through a per-warp
 //     global scratch that stays L2 resident (8 B per column).
-//   * all values carry the bias a + beta_t (a = open+ext, beta_t grows by ext per step): F-ext is a plain 32-bit
-//     add with no borrow between the halves (FMA pipe, IMAD), E-ext needs no instruction at all, and the zero
-//     floor of local alignment is a register. Per packed cell pair: 4.5 DPX instructions on the ALU pipe
-//     (VIADDMNMX.S16x2 x3, VIMNMX3.S16x2 x1.5) + 1 IMAD.
+//   * every stored value of (step t, strip row k) is  true value + a + (t - tbase + k) * ext  -- an anti-diagonal
+//     bias: a value that moves one column to the right (E) or one row down (F) meets a bias that is ext larger,
+//     so BOTH gap extensions cost no instruction; the zero floor of local alignment becomes a sliding window of
+//     registers FL[u + k] computed on the FMA pipe. Per packed cell pair 4 DPX instructions on the ALU pipe:
+//         x  = VIADDMNMX.S16x2(Hdiag, S + 2*ext, E)        max(Hdiag + S, E)
+//         H  = VIMNMX3.S16x2  (x, FL, F)                   max(x, F, 0)
+//         E' = VIADDMNMX.S16x2(H, ext - open, E)           max(H - open, E - ext)
+//         F' = VIADDMNMX.S16x2(H, ext - open, F)           max(H - open, F - ext)
+//     plus 1 DPX per 8 cells for the sampled running maximum. a = open + ext (sw_bias) keeps the low half of every
+//     value that is touched by a plain 32-bit add non-negative, so no borrow crosses the halves; the bias is
+//     rebased at chunk boundaries before 16 bits could overflow.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -40,10 +47,17 @@ constexpr int kWarpsPerBlock = NMSV_WPB;   // independent warps per block (each 
 #define NMSV_WARPS_PER_SM 16
 #endif
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxR = 32;          // largest strip height of any instantiation (head-room formula below)
+
+// a: constant part of the bias
+__host__ __device__ constexpr int sw_bias(int open, int ext) { return open + ext; }
+// 16-bit head-room a template needs on top of match * rows: the bias constant, one chunk of steps between two
+// rebases plus the 4-step unroll, and the row part of the bias. The host rejects longer templates (NMSV_E_RANGE).
+__host__ __device__ constexpr int sw_headroom(int open, int ext) { return sw_bias(open, ext) + ext + (kChunk + 4 + kMaxR) * ext; }
 
 enum : uint32_t { kARev = 1u, kAComp = 2u, kBRev = 4u, kBComp = 8u, kCRev = 16u };
 
-struct SwTask {          // 48 bytes
+struct SwTask {          // 64 bytes
     uint64_t a_base;     // index into codes of row 0 of half A (row i is a_base +/- i)
     uint64_t b_base;
     uint64_t c_base;     // index of column 0 (column j is c_base +/- j)
@@ -53,13 +67,27 @@ struct SwTask {          // 48 bytes
     uint32_t flags;
     uint32_t out;        // index into results
     uint32_t rclass;     // strip height R of the kernel instantiation that owns this task
+    uint32_t best0;      // half A: score the answer is known to have (begin pass: the forward score), 0 = unknown.
+                         // The running maximum then starts at best0 - 1, so that only the cells that reach best0 --
+                         // the candidates for the begin cell -- take the exact path instead of every cell of the
+                         // climb along the alignment.
+    uint32_t pad_[3];
 };
+
+static_assert(sizeof(SwTask) == 64, "the dynamic queue reads a task as four 16-byte words");
 
 struct SwResult {        // [0] = half A, [1] = half B ; row/col 0-based in the task's own orientation
     int32_t score[2];
     int32_t row[2];
     int32_t col[2];
 };
+
+// Continuation of a task group (validate path): when the last forward task of a read has finished, lane 0 of that warp
+// calls sw_group_done(), which applies the decision rules to the read and appends its begin-pass tasks to a dynamic
+// queue that the same persistent launch drains -- the begin pass fills the tail of the forward pass instead of running
+// as an under-occupied launch of its own. Defined by the translation unit that includes this header.
+struct GroupHook;
+__device__ void sw_group_done(const GroupHook* hook, uint32_t out);
 
 struct SwParams {
     const uint8_t* codes;
@@ -74,6 +102,14 @@ struct SwParams {
     uint32_t neg_open2;     // (-open, -open) packed: DPX add operand, read from the constant bank
     uint32_t ext_m_open2;   // (ext-open, ext-open) packed
     uint32_t ext2;          // ext * 65537
+    // ---- optional continuation (all null/0 for independent tasks)
+    const GroupHook* hook;          // device pointer
+    uint32_t* group_remaining;      // [task.out >> 2] tasks of the group still to finish (set up before the launch)
+    const SwTask* dyn_tasks;        // dynamic queue of this strip class: entries [0, *dyn_reserve), entry i valid once
+    const uint32_t* dyn_ready;      //   dyn_ready[i] != 0; *dyn_head = next entry to hand out
+    const uint32_t* dyn_reserve;
+    uint32_t* dyn_head;
+    SwResult* dyn_results;
 };
 
 template <int R>
@@ -167,6 +203,48 @@ __device__ __forceinline__ void warp_argbest(int& s, int& c, int& r)
     }
 }
 
+// Task acquisition, kept out of line: its data-dependent loops would otherwise cost the kernel body the compiler's
+// convergence analysis (BRA.DIV before every shuffle of the hot loop). Nothing here waits for work to appear: a warp
+// that finds both queues empty leaves, and whatever is queued later is run by the follow-up launch over the same queue.
+__device__ __noinline__ uint32_t sw_pick_task(uint32_t* queue_head, uint32_t n_tasks, uint32_t* dyn_head,
+                                           const uint32_t* dyn_reserve, const uint32_t* dyn_ready)
+{
+    uint32_t src = 0, ti = 0;
+    if ((threadIdx.x & 31) == 0) {
+        if (dyn_reserve) {
+            uint32_t h = *reinterpret_cast<volatile uint32_t*>(dyn_head);
+            while (h < *reinterpret_cast<const volatile uint32_t*>(dyn_reserve)) {
+                const uint32_t o = atomicCAS(dyn_head, h, h + 1u);
+                if (o == h) { src = 2; ti = h; break; }
+                h = o;
+            }
+            // the producer publishes dyn_ready[ti] right after the task body (fence in between); it is a running warp
+            // between two adjacent statements, so this wait is a few hundred nanoseconds at most
+            if (src == 2) {
+                while (*reinterpret_cast<const volatile uint32_t*>(dyn_ready + ti) == 0u) __nanosleep(64);
+                __threadfence();
+            }
+        }
+        if (!src) {
+            ti = atomicAdd(queue_head, 1u);
+            if (ti < n_tasks) src = 1;
+        }
+    }
+    __syncwarp();
+    return src == 0 ? 0xffffffffu : (src == 2 ? (ti | 0x80000000u) : ti);
+}
+
+// lane 0, after the result of a static task is stored: count the task's group down and run the continuation when
+// this was its last task
+__device__ __noinline__ void sw_task_done(const GroupHook* hook, uint32_t* group_remaining, uint32_t out)
+{
+    __threadfence();        // the result before the count
+    if (atomicSub(&group_remaining[out >> 2], 1u) == 1u) {
+        __threadfence();    // the other tasks' results after their counts
+        sw_group_done(hook, out);
+    }
+}
+
 // OPEN/EXT >= 0: gap penalties known at compile time (the reference always calls parasail.ssw(.., 3, 1, ..),
 // count_sread_by_alignment.py:148): the DPX add operands become immediates, which saves one vector-register read on
 // two of the 4.5 DPX instructions per cell pair. OPEN = EXT = -1: generic instantiation, operands from the parameters.
@@ -193,7 +271,7 @@ sw_wavefront_kernel(const SwParams p)
     //   * a keeps E - ext and F - ext non-negative in the low half, so they are plain 32-bit adds (FMA pipe);
     //   * beta grows by ext per step, which turns  E' = max(H - open, E - ext)  into  max(H + (ext - open), E):
     //     the horizontal gap extension costs no instruction at all. beta is rebased at chunk boundaries.
-    const int bias = p.open + p.ext;
+    const int bias = sw_bias(p.open, p.ext);
     const uint32_t FLOOR0 = pack16(bias, bias);
     const uint32_t EF0 = pack16(bias - p.open, bias - p.open);          // E = F = -open
     constexpr bool kFixedGaps = (OPEN >= 0 && EXT >= 0);
@@ -203,9 +281,11 @@ sw_wavefront_kernel(const SwParams p)
     // lane 0 takes H/F of the row above its strip from the boundary ring, lanes 1..31 from lane-1 by shuffle. Instead
     // of two SELs (ALU pipe) per step every lane does  in = shfl * m1 + ld  (IMAD): lane 0 has m1 = 0 and loads the
     // ring entry of this step, the others have m1 = 1 and load a constant slot holding +ext (the bias lift).
-    const uint32_t m1 = is_lane0 ? 0u : 1u;
+    uint32_t m1 = is_lane0 ? 0u : 1u;
+    asm volatile("" : "+r"(m1));           // opaque: keeps ptxas from re-deriving it from the lane id inside the loop
     const char* const bsrc = is_lane0 ? reinterpret_cast<const char*>(bring) : reinterpret_cast<const char*>(bconst);
-    const uint32_t bstride = is_lane0 ? 8u : 0u;
+    uint32_t bstride = is_lane0 ? 8u : 0u;
+    asm volatile("" : "+r"(bstride));      // opaque: otherwise ptxas specialises the address arithmetic with predicated moves
     // read ring: column j lives at rring[j % kRing] and again kRing bytes later; lane l reads (t % kRing) + kRing - l
     const uint8_t* const rlane = rring + kRing - lane;
     if (lane == 0) {
@@ -216,11 +296,23 @@ sw_wavefront_kernel(const SwParams p)
     uint32_t tma_parity = 0;       // phase of the next mbarrier completion to wait for
 
     for (;;) {
-        uint32_t ti = 0;
-        if (lane == 0) ti = atomicAdd(p.queue_head, 1u);
-        ti = __shfl_sync(kFull, ti, 0);
-        if (ti >= n_tasks) break;
-        const SwTask task = p.tasks[ti];
+        // ---- next task: the dynamic queue first (begin tasks of reads that are already decided), then the static list
+#ifdef NMSV_NO_CONTINUATION
+        uint32_t code = 0xffffffffu;
+        if (lane == 0) { code = atomicAdd(p.queue_head, 1u); if (code >= n_tasks) code = 0xffffffffu; }
+#else
+        uint32_t code = sw_pick_task(p.queue_head, n_tasks, p.dyn_head, p.dyn_reserve, p.dyn_ready);
+#endif
+        code = __shfl_sync(kFull, code, 0);
+        if (code == 0xffffffffu) break;
+        const uint32_t src = (code >> 31) + 1u, ti = code & 0x7fffffffu;
+        // one load path for both lists, through L2 (a line of the dynamic queue may be stale in L1)
+        const uint4* q = reinterpret_cast<const uint4*>((src == 1 ? p.tasks : p.dyn_tasks) + ti);
+        const uint4 w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2), w3 = __ldcg(q + 3);
+        SwTask task;
+        task.a_base = ((uint64_t)w0.y << 32) | w0.x; task.b_base = ((uint64_t)w0.w << 32) | w0.z;
+        task.c_base = ((uint64_t)w1.y << 32) | w1.x; task.a_len = w1.z; task.b_len = w1.w;
+        task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w; task.best0 = w3.x;
         if (task.rclass != (uint32_t)R || task.ncols == 0) continue;
 
         const int a_len = (int)task.a_len, b_len = (int)task.b_len, ncols = (int)task.ncols;
@@ -231,11 +323,15 @@ sw_wavefront_kernel(const SwParams p)
         const int ntiles = (rows + 32 * R - 1) / (32 * R);
         const int total_steps = (ncols + 31 + 3) & ~3;   // multiple of 4: the step body is unrolled 4x (pad steps are inert)
         // steps the bias may run before the 16-bit lanes could overflow (host guarantees >= kChunk)
-        const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext - R - 4 : 0x7fffffff;
+        const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext - kMaxR - 4 : 0x7fffffff;
 
         // running best over tiles, per half: {score, col, row}
         int bs0 = 0, bc0 = 0, br0 = a_len - 1;
+        if (task.best0) { bs0 = (int)task.best0; bc0 = 0x7fffffff; br0 = 0x7fffffff; }   // a cell reaching best0 ties and wins by column
         int bs1 = 0, bc1 = 0, br1 = b_len - 1;
+        // An unused half (begin pass) holds the floor in every cell: with a running maximum of 0 every cell would sit
+        // within the sampling margin and send the warp down the exact path at every step. Park its maximum out of reach.
+        if (b_len == 0) bs1 = 256;
 
         for (int tile = 0; tile < ntiles; ++tile) {
             const int row0 = tile * 32 * R + lane * R;
@@ -286,11 +382,13 @@ sw_wavefront_kernel(const SwParams p)
             // prefetched is a pure function of t0 (a mutable flag would cost the compiler its uniformity analysis)
             const bool tma_task = !c_rev && ((task.c_base & 15ull) == 0);
 
-            // Filter threshold for TWO consecutive columns at once: no row of either column exceeds the running maximum
-            // if no sampled row comes within open + 2*ext of it; the older column is compared one ext too strictly.
+            // Filter threshold for TWO consecutive columns at once: an unsampled row lies at most stride-1 rows above a
+            // sampled one and exceeds its H by at most open + (stride-2)*ext; the older column is compared at the newer
+            // column's bias, i.e. one ext too strictly, hence open + (stride-1)*ext.
 #ifndef NMSV_SAMPLE_STRIDE
 #define NMSV_SAMPLE_STRIDE 4
 #endif
+            static_assert(NMSV_SAMPLE_STRIDE >= 2 && NMSV_SAMPLE_STRIDE <= 4, "the threshold must stay non-negative: a + 2*ext >= margin");
             const uint32_t MARGIN2 = (uint32_t)((p.open + (NMSV_SAMPLE_STRIDE - 1) * ext) * 65537);
             // One column. tq = t - U is a multiple of 4, so every ring index of step t is a base computed once per four
             // steps plus the compile-time constant U (no per-step uniform-datapath arithmetic).
@@ -326,14 +424,14 @@ sw_wavefront_kernel(const SwParams p)
             };
             // ---- running maximum after a pair of columns (older column in Ha, newer in Hb; t = step of the older).
             // Rows k and k' <= k of one column satisfy H[k] >= H[k'] - open - (k-k'-1)*ext (through F), so if no row
-            // of {R-1, R-5, ...} comes within the margin of the running maximum no row of the strip exceeds it:
-            // 1 DPX per 8 rows and column instead of 1 per 2 rows in the common case.
+            // of {R-1, R-1-stride, ...} comes within the margin of the running maximum no row of the strip exceeds it:
+            // 1 DPX per `stride` rows and column in the common case.
             auto negk = [&](const int k) -> uint32_t {      // (-k*ext, -k*ext): removes the row part of the bias
                 return kFixedGaps ? (((uint32_t)(-k * EXT)) & 0xffffu) * 65537u : (((uint32_t)(-k * ext)) & 0xffffu) * 65537u;
             };
             auto track = [&](const uint32_t (&Ha)[R], const uint32_t (&Hb)[R], const int t) {
                 const uint32_t bp2 = add_halves(bestprev, 2 * ext);      // running maximum at the newer step's row-0 bias
-                const uint32_t thr = bp2 - MARGIN2;                       // floors >= open + 2*ext: no borrow
+                const uint32_t thr = bp2 - MARGIN2;                       // bp2 >= a + 2*ext = open + 3*ext in both halves: no borrow
                 uint32_t q = thr;
 #pragma unroll
                 for (int k = R - 1; k >= 0; k -= NMSV_SAMPLE_STRIDE) {
@@ -495,8 +593,11 @@ sw_wavefront_kernel(const SwParams p)
         if (lane == 0) {
             SwResult res;
             res.score[0] = bs0; res.row[0] = br0; res.col[0] = bc0;
-            res.score[1] = bs1; res.row[1] = br1; res.col[1] = bc1;
-            p.results[task.out] = res;
+            res.score[1] = b_len ? bs1 : 0; res.row[1] = br1; res.col[1] = bc1;
+            (src == 1 ? p.results : p.dyn_results)[task.out] = res;
+#ifndef NMSV_NO_CONTINUATION
+            if (src == 1 && p.hook) sw_task_done(p.hook, p.group_remaining, task.out);
+#endif
         }
     }
 }

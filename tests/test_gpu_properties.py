@@ -150,3 +150,28 @@ def test_bias_rebase_on_very_long_reads(engine):
     f = engine.ssw_batch(pack, [t], [r])[0]
     assert (int(f["score1"]), int(f["read_begin1"]), int(f["read_end1"]), int(f["ref_begin1"]), int(f["ref_end1"])) == \
            (28000, 0, 13999, 9000, 22999)
+
+
+def test_longest_accepted_template_is_exact(engine):
+    """The host rejects templates whose scores could leave the 16-bit range including the kernel's bias head-room
+    (NMSV_E_RANGE, like parasail's None). The longest template it accepts forces a bias rebase at every chunk and must
+    still be exact; one base more must be refused, for every strip height."""
+    from nanomonsv_b200.engine import EngineError
+    rng = np.random.default_rng(17)
+    # match * len + headroom <= 32767 - match - 1 with headroom = (open + ext) + ext + (128 + 4 + 32) * ext = 169
+    lmax = (32767 - 2 - 1 - 169) // 2
+    tmpl = _rand(rng, lmax)
+    body = np.concatenate((_rand(rng, 700), tmpl, _rand(rng, 900)))
+    pack = SeqPack()
+    t, r, trc = pack.add_codes(tmpl), pack.add_codes(body), pack.add_codes(synth.revcomp_codes(tmpl))
+    f = engine.ssw_batch(pack, [t], [r])[0]
+    assert (int(f["score1"]), int(f["read_begin1"]), int(f["read_end1"]), int(f["ref_begin1"]), int(f["ref_end1"])) == \
+           (2 * lmax, 0, lmax - 1, 700, 700 + lmax - 1)
+    a = engine.ssw_check_batch(pack, [trc], [r])[0]
+    assert (int(a["score"]), int(a["strand"]), int(a["qstart"]), int(a["qend"])) == (2 * lmax, -1, 1, lmax)
+    pack = SeqPack()
+    t, r = pack.add_codes(_rand(rng, lmax + 1)), pack.add_codes(body)
+    with pytest.raises(EngineError) as e:
+        engine.ssw_batch(pack, [t], [r])
+    assert e.value.code == _lib.E_RANGE
+

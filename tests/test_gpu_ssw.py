@@ -154,6 +154,40 @@ def test_long_reads_up_to_50kb(engine):
         _assert_same(r, a, b)
 
 
+def test_begin_window_covers_long_insertions(engine):
+    """The begin pass visits a bounded window of reversed columns (rows + (match*rows - score) / min(open, ext)): reads
+    that carry a long insertion inside the template -- the optimal local alignment spans far more columns than rows --
+    must still give the begin cell of the full rectangle."""
+    rnd = random.Random(909)
+    pairs, tmpls = [], []
+    for m, ins in ((600, 250), (400, 150), (2000, 700), (1200, 160), (1200, 140)):
+        a = "".join(rnd.choice("ACGT") for _ in range(m))
+        cut = m // 2 + rnd.randint(-20, 20)
+        for strand in (1, -1):
+            src = a if strand > 0 else O.reverse_complement(a)
+            b = "".join(rnd.choice("ACGT") for _ in range(rnd.randint(100, 900))) + _mutated_copy(rnd, src[:cut], 0.03) + \
+                "".join(rnd.choice("ACGT") for _ in range(ins)) + _mutated_copy(rnd, src[cut:], 0.03) + \
+                "".join(rnd.choice("ACGT") for _ in range(rnd.randint(100, 900)))
+            pairs.append((src, b))
+            tmpls.append(a)
+    res = _gpu_pairs(engine, pairs)
+    spans = 0
+    for (a, b), r in zip(pairs, res):
+        _assert_same(r, a, b)
+        rows = int(r["read_end1"]) - int(r["read_begin1"]) + 1
+        cols = int(r["ref_end1"]) - int(r["ref_begin1"]) + 1
+        spans += cols > rows + rows // 8 + 64
+    assert spans >= 6          # the insertion really is inside most alignments
+    pack = SeqPack()
+    t = [pack.add(a) for a in tmpls]          # the template itself: every second read holds its reverse complement
+    rd = [pack.add(b) for _, b in pairs]
+    chk = engine.ssw_check_batch(pack, t, rd)
+    for a, (_, b), c in zip(tmpls, pairs, chk):
+        exp = O.ssw_check(a, [("r", b)])["r"]
+        assert [int(c["score"]), int(c["qstart"]), int(c["qend"]), int(c["tstart"]), int(c["tend"]), "+" if c["strand"] > 0 else "-"] == exp
+    assert sorted(int(c["strand"]) for c in chk) == [-1] * 5 + [1] * 5
+
+
 @pytest.mark.parametrize("scoring", [(1, -2, 3, 1), (2, -3, 5, 2), (3, -1, 2, 2), (2, -2, 3, 3), (2, 0, 4, 1)])
 def test_other_scorings(engine, scoring):
     """The other parasail.ssw call sites use other matrices (locate_bp_sbnd.py:28 uses 1/-2)."""

@@ -189,3 +189,32 @@ def test_ssw_check_file_seam(engine, tmp_path):
     got = C.ssw_check(str(q), str(t), False, engine=engine)
     exp = O.ssw_check("ACGTTTTTACGT", list(O.fasta_records(str(t))))
     assert got == exp and set(got) == {"r1", "r2"}
+
+
+def test_fused_and_separate_begin_pass_agree(engine, monkeypatch):
+    """By default the forward launches also drain the begin-pass queue that the per-read continuation fills
+    (DESIGN.md "fused begin pass"); NMSV_FUSED_BEGIN=0 runs decide and the begin pass as launches of their own. Both
+    must produce identical counts, records and alignment tuples -- on a canonical workload (one strip class) and on a
+    single-breakend one (two strip classes: 601- and 400-base templates), and on repeated runs of one plan."""
+    for preset, kw in (("testdata_shaped", dict(n_sv=10, coverage=10.0, short_fraction=0.5, seed=311)),
+                       ("single_breakend", dict(n_sv=8, coverage=10.0, seed=312))):
+        cfg = dataclasses.replace(synth.PRESETS[preset], read_len_mean=2500, read_len_min=500, read_len_max=8000,
+                                  contig_len=150000, n_contigs=2, **kw)
+        wl = synth.make_workload(cfg)
+        pack, svs, reads = wl.to_batch("tumor", var_read_min_mapq=0)
+        out = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("NMSV_FUSED_BEGIN", mode)
+            plan = engine.plan(pack, svs, reads)
+            for _ in range(2):
+                plan.run()
+            checked, supporting, records = plan.download()
+            alns, flags = plan.download_alns()
+            st = plan.stats()
+            assert st["kernel_launches"] == (2 if mode == "1" else 3) + 2 * st["n_classes"]
+            out[mode] = (checked, supporting, records, alns, flags, st["rev_tasks"])
+            plan.close()
+        a, b = out["1"], out["0"]
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
+        assert (a[3] == b[3]).all() and (a[4] == b[4]).all() and a[5] == b[5] > 0
+        assert int(a[1].sum()) > 0
