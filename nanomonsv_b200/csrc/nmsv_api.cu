@@ -64,6 +64,7 @@ struct nmsv_ctx {
     cudaDeviceProp prop;
     int sm_clock_khz = 0;
     int blocks_per_sm[8] = {0};
+    void* snap = nullptr;      // per resident warp: column snapshots of the running-maximum tracker (nmsv_sw.cuh)
     mutable std::string error;
 };
 
@@ -190,6 +191,11 @@ extern "C" int nmsv_create(nmsv_ctx** out, int device)
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (int c = 0; c < kNumClasses; ++c) CREATE_TRY(setup_class_idx(c, &ctx->blocks_per_sm[c]));
+    {
+        int g = 0;
+        for (int c = 0; c < kNumClasses; ++c) g = std::max(g, ctx->prop.multiProcessorCount * std::max(1, ctx->blocks_per_sm[c]));
+        CREATE_TRY(cudaMalloc(&ctx->snap, (size_t)g * kWarpsPerBlock * kSnapWords * 32 * sizeof(uint4)));
+    }
     {   // keep freed blocks cached in the stream-ordered pool: plans are created and destroyed per batch
         cudaMemPool_t pool;
         CREATE_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -206,6 +212,7 @@ extern "C" void nmsv_destroy(nmsv_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
+    if (ctx->snap) cudaFree(ctx->snap);
     delete ctx;
 }
 
@@ -921,7 +928,7 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     SwParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.codes = pl->st.codes.as<uint8_t>();
-    sp.bnd = pl->bnd.as<uint2>(); sp.bnd_stride = pl->bnd_stride;
+    sp.bnd = pl->bnd.as<uint2>(); sp.bnd_stride = pl->bnd_stride; sp.snap = (uint4*)ctx->snap;
     sp.match = pl->sc.match; sp.mismatch = pl->sc.mismatch; sp.open = pl->sc.gap_open; sp.ext = pl->sc.gap_extend;
     fill_packed(sp);
 
@@ -1165,7 +1172,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     pair_plan_kernel<<<nb, tpb, 0, s>>>(pp, tasks.as<SwTask>());
     SwParams sp;
     memset(&sp, 0, sizeof(sp));
-    sp.codes = st.codes.as<uint8_t>(); sp.bnd = bnd.as<uint2>(); sp.bnd_stride = stride;
+    sp.codes = st.codes.as<uint8_t>(); sp.bnd = bnd.as<uint2>(); sp.bnd_stride = stride; sp.snap = (uint4*)ctx->snap;
     sp.match = sc->match; sp.mismatch = sc->mismatch; sp.open = sc->gap_open; sp.ext = sc->gap_extend;
     fill_packed(sp);
     sp.tasks = tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = n_pairs; sp.results = fwd.as<SwResult>();

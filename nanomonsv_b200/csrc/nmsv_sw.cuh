@@ -47,6 +47,7 @@ constexpr int kWarpsPerBlock = NMSV_WPB;   // independent warps per block (each 
 #define NMSV_WARPS_PER_SM 16
 #endif
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSnapWords = 2 * (32 / 4 + 1);   // per lane and half: up to 32 rows as uint4 + one word (maximum before, step)
 constexpr int kMaxR = 32;          // largest strip height of any instantiation (head-room formula below)
 
 // a: constant part of the bias
@@ -98,6 +99,7 @@ struct SwParams {
     SwResult* results;
     uint2* bnd;                    // [grid warps][bnd_stride] tile-boundary scratch (H, F of a tile's last row)
     uint32_t bnd_stride;
+    uint4* snap;                   // [grid warps][kSnapWords * 32] column snapshots of the running-maximum tracker
     int match, mismatch, open, ext;
     uint32_t neg_open2;     // (-open, -open) packed: DPX add operand, read from the constant bank
     uint32_t ext_m_open2;   // (ext-open, ext-open) packed
@@ -265,6 +267,7 @@ sw_wavefront_kernel(const SwParams p)
     uint8_t* rring = reinterpret_cast<uint8_t*>(bconst + 4);
     const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + warp;
     uint2* const bnd0 = p.bnd + (size_t)gwarp * p.bnd_stride;
+    uint4* const snap_lane = p.snap + (size_t)gwarp * (kSnapWords * 32) + lane;    // word w of half h: [(h * (G+1) + w) * 32]
 
     const uint32_t n_tasks = p.n_tasks_dev ? *p.n_tasks_dev : p.n_tasks;
     // Every stored H/E/F value is  true value + a + beta_t  with a = open + ext and beta_t = (t - tbase) * ext:
@@ -288,6 +291,11 @@ sw_wavefront_kernel(const SwParams p)
     asm volatile("" : "+r"(bstride));      // opaque: otherwise ptxas specialises the address arithmetic with predicated moves
     // read ring: column j lives at rring[j % kRing] and again kRing bytes later; lane l reads (t % kRing) + kRing - l
     const uint8_t* const rlane = rring + kRing - lane;
+    // ext once more, in a vector register: as a uniform value ptxas re-materialises it with a move per use inside the
+    // hot loop. A value that went through shared memory is not uniform in its eyes.
+    if (lane == 0) bconst[1] = make_uint2((uint32_t)p.ext, 0u);
+    __syncwarp();
+    const uint32_t ext_v = reinterpret_cast<const volatile uint2*>(bconst)[1].x;
     if (lane == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -297,12 +305,7 @@ sw_wavefront_kernel(const SwParams p)
 
     for (;;) {
         // ---- next task: the dynamic queue first (begin tasks of reads that are already decided), then the static list
-#ifdef NMSV_NO_CONTINUATION
-        uint32_t code = 0xffffffffu;
-        if (lane == 0) { code = atomicAdd(p.queue_head, 1u); if (code >= n_tasks) code = 0xffffffffu; }
-#else
         uint32_t code = sw_pick_task(p.queue_head, n_tasks, p.dyn_head, p.dyn_reserve, p.dyn_ready);
-#endif
         code = __shfl_sync(kFull, code, 0);
         if (code == 0xffffffffu) break;
         const uint32_t src = (code >> 31) + 1u, ti = code & 0x7fffffffu;
@@ -375,7 +378,6 @@ sw_wavefront_kernel(const SwParams p)
             // later tiles start their running maximum at (best of the earlier tiles - 1), per half
             uint32_t bestprev = FLOOR0 + pack16(bs0 > 0 ? bs0 - 1 : 0, bs1 > 0 ? bs1 - 1 : 0);
             uint32_t flb = FLOOR0 + p.ext2;     // floor of row k at step t is flb + (t+k)*ext2 = FLOOR0 + (t - tbase + k)*ext2
-            int col_lo = 0, row_lo = 0, col_hi = 0, row_hi = 0;   // only meaningful once best rose above the floor
             uint32_t h_last = FLOOR0 + (uint32_t)(R - 1) * p.ext2, f_out = EF0 + (uint32_t)R * p.ext2, diag = FLOOR0 - p.ext2;
             int tbase = -1;          // bias of row k at step t = (t - tbase + k) * ext ; "after step -1" row 0 carries 0
             // TMA staging applies to forward reads that start on a 16-byte boundary; whether a given chunk was
@@ -429,6 +431,34 @@ sw_wavefront_kernel(const SwParams p)
             auto negk = [&](const int k) -> uint32_t {      // (-k*ext, -k*ext): removes the row part of the bias
                 return kFixedGaps ? (((uint32_t)(-k * EXT)) & 0xffffu) * 65537u : (((uint32_t)(-k * ext)) & 0xffffu) * 65537u;
             };
+            auto snap_store = [&](const int h, const uint32_t (&Hx)[R], const uint32_t before, const int step) {
+                uint4* d = snap_lane + h * (G + 1) * 32;
+#pragma unroll
+                for (int g = 0; g < G; ++g)
+                    __stcg(d + g * 32, make_uint4(Hx[4 * g], 4 * g + 1 < R ? Hx[(4 * g + 1) % R] : 0u,
+                                                  4 * g + 2 < R ? Hx[(4 * g + 2) % R] : 0u, 4 * g + 3 < R ? Hx[(4 * g + 3) % R] : 0u));
+                __stcg(d + G * 32, make_uint4(before, (uint32_t)step, 0u, 0u));
+            };
+            // (column, row) of the first cell of the saved column that holds its maximum, for half h
+            auto resolve_snap = [&](const int h, int& col, int& row) {
+                const uint4* d = snap_lane + h * (G + 1) * 32;
+                const uint4 meta = __ldcg(d + G * 32);
+                const int sh = 16 * h;
+                int bestv = (int)(int16_t)(meta.x >> sh), r = 0;
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    const uint4 v = __ldcg(d + g * 32);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = 4 * g + i;
+                        const int hv = (int)(int16_t)(w[i] >> sh) - k * ext;      // row part of the bias removed
+                        if (k < R && hv > bestv) { bestv = hv; r = k; }
+                    }
+                }
+                col = (int)meta.y - lane;
+                row = row0 + r;
+            };
             auto track = [&](const uint32_t (&Ha)[R], const uint32_t (&Hb)[R], const int t) {
                 const uint32_t bp2 = add_halves(bestprev, 2 * ext);      // running maximum at the newer step's row-0 bias
                 const uint32_t thr = bp2 - MARGIN2;                       // bp2 >= a + 2*ext = open + 3*ext in both halves: no borrow
@@ -440,35 +470,26 @@ sw_wavefront_kernel(const SwParams p)
                 }
                 uint32_t best = bp2;
                 if (q != thr) {
-                    // rare: some row may exceed this lane's running maximum. One prefix-maximum pass per column: VIMNMX
-                    // with predicate outputs tells per half whether H[k] strictly beats everything before it; the
-                    // last such row is the first row holding the column maximum (parasail: smallest row). The running
-                    // value follows the row bias (+ext per row) and is brought back to row 0 afterwards.
-                    best = add_halves(bestprev, ext);
-                    int rl = -1, rh = -1;
+                    // rare: some row may exceed this lane's running maximum. Only the LAST rise of a lane can be the
+                    // answer, and most rises are followed by another one a column later (the climb along the
+                    // alignment), so the position is not worked out here: the exact new maximum is computed (one DPX per
+                    // row), and for each half that rose the column it rose in is saved to a per-lane scratch slot together
+                    // with the maximum before that column and the step; the slot is examined once, at the end of the
+                    // tile (resolve_snap). A later tie does not rise and leaves the slot alone: first column wins.
+                    const uint32_t b0 = add_halves(bestprev, ext);        // running maximum at (older step, row 0)
+                    uint32_t ma = b0;
 #pragma unroll
-                    for (int k = 0; k < R; ++k) {
-                        bool keep_hi, keep_lo;                       // keep_* = (best >= H[k]) in that half
-                        if (k > 0) best = add_halves(best, ext);
-                        best = __vibmax_s16x2(best, Ha[k], &keep_hi, &keep_lo);
-                        if (!keep_lo) rl = k;
-                        if (!keep_hi) rh = k;
-                    }
-                    if (rl >= 0) { col_lo = t - lane; row_lo = row0 + rl; }
-                    if (rh >= 0) { col_hi = t - lane; row_hi = row0 + rh; }
-                    best = add_halves(best, ext - (R - 1) * ext);      // back to row 0, then on to the newer step
-                    rl = -1; rh = -1;
+                    for (int k = 0; k < R; ++k) ma = __viaddmax_s16x2(Ha[k], negk(k), ma);
+                    const uint32_t mb0 = add_halves(ma, ext);             // ... at (newer step, row 0)
+                    uint32_t mb = mb0;
 #pragma unroll
-                    for (int k = 0; k < R; ++k) {
-                        bool keep_hi, keep_lo;
-                        if (k > 0) best = add_halves(best, ext);
-                        best = __vibmax_s16x2(best, Hb[k], &keep_hi, &keep_lo);
-                        if (!keep_lo) rl = k;
-                        if (!keep_hi) rh = k;
-                    }
-                    if (rl >= 0) { col_lo = t + 1 - lane; row_lo = row0 + rl; }
-                    if (rh >= 0) { col_hi = t + 1 - lane; row_hi = row0 + rh; }
-                    best = add_halves(best, -(R - 1) * ext);
+                    for (int k = 0; k < R; ++k) mb = __viaddmax_s16x2(Hb[k], negk(k), mb);
+                    const uint32_t ra = ma ^ b0, rb = mb ^ mb0;           // non-zero half: that half rose in that column
+                    if (rb & 0xffffu) snap_store(0, Hb, mb0, t + 1);
+                    else if (ra & 0xffffu) snap_store(0, Ha, b0, t);
+                    if (rb >> 16) snap_store(1, Hb, mb0, t + 1);
+                    else if (ra >> 16) snap_store(1, Ha, b0, t);
+                    best = mb;
                 }
                 bestprev = best;
             };
@@ -537,7 +558,8 @@ sw_wavefront_kernel(const SwParams p)
                         uint32_t FL[R + 3];      // floors of (step t+u, row k) = FL[u + k]: warp-uniform sliding window
                         FL[0] = flb + (uint32_t)t * p.ext2;
 #pragma unroll
-                        for (int i = 1; i < R + 3; ++i) FL[i] = add_halves(FL[i - 1], ext);     // IMAD chain, FMA pipe
+                        for (int i = 1; i < R + 3; ++i)      // IMAD chain, FMA pipe
+                            asm("mad.lo.u32 %0, %1, 65537, %2;" : "=r"(FL[i]) : "r"(ext_v), "r"(FL[i - 1]));
                         const char* bq = bsrc + (uint32_t)(t & (kChunk - 1)) * bstride;
                         const uint8_t* rq = rlane + (t & (kRing - 1));
                         uint2* sq = bstage + (t & 31);
@@ -580,11 +602,16 @@ sw_wavefront_kernel(const SwParams p)
 
             // ---- tile epilogue: warp arg-best per half, merge into the running best (later tiles hold larger rows)
             const uint32_t fl = flb + (uint32_t)(total_steps - 1) * p.ext2;     // floor of the last step
-            int s = (int)(bestprev & 0xffffu) - (int)(fl & 0xffffu), c = col_lo, r = row_lo;
+            // Every lane resolves its slots, whether it wrote them in this tile or not (a per-lane "valid" flag would
+            // cost the compiler its convergence analysis of the loop above): a lane that holds the warp-wide maximum rose
+            // to it in this tile, so its slot is current; any other lane loses the arg-best below whatever it reads.
+            int s = (int)(bestprev & 0xffffu) - (int)(fl & 0xffffu), c = 0, r = 0;
+            resolve_snap(0, c, r);
             if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
             warp_argbest(s, c, r);
             if (s > bs0 || (s == bs0 && s > 0 && c < bc0)) { bs0 = s; bc0 = c; br0 = r; }
-            s = (int)(bestprev >> 16) - (int)(fl >> 16); c = col_hi; r = row_hi;
+            s = (int)(bestprev >> 16) - (int)(fl >> 16);
+            resolve_snap(1, c, r);
             if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
             warp_argbest(s, c, r);
             if (s > bs1 || (s == bs1 && s > 0 && c < bc1)) { bs1 = s; bc1 = c; br1 = r; }
@@ -595,9 +622,7 @@ sw_wavefront_kernel(const SwParams p)
             res.score[0] = bs0; res.row[0] = br0; res.col[0] = bc0;
             res.score[1] = b_len ? bs1 : 0; res.row[1] = br1; res.col[1] = bc1;
             (src == 1 ? p.results : p.dyn_results)[task.out] = res;
-#ifndef NMSV_NO_CONTINUATION
             if (src == 1 && p.hook) sw_task_done(p.hook, p.group_remaining, task.out);
-#endif
         }
     }
 }
