@@ -34,9 +34,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # DPX lane-instructions per DP cell on the hot path of sw_wavefront_kernel<16,3,1>: per step and lane 16 packed
-# (template, revcomp) cell pairs cost 48 VIADDMNMX.S16x2 + 16 VIMNMX3.S16x2 (x, H, E', F') + 4 VIADDMNMX.S16x2 for
-# the sampled running maximum = 68 instructions per 32 cells (SASS count)
-DPX_PER_CELL = 68.0 / 32.0
+# (template, revcomp) cell pairs cost 48 VIADDMNMX.S16x2 + 16 VIMNMX3.S16x2 (x, H, E', F') + 2 VIADDMNMX.S16x2 for
+# the sampled running maximum = 66 instructions per 32 cells (SASS count)
+DPX_PER_CELL = 66.0 / 32.0
 WORKLOAD = "colo829_shaped"
 # mean EXECUTED forward cells of one synthetic candidate (tumor + control reads, both strands, m = 2000, identical
 # templates counted once), measured on the generator; the per-GPU batch is cut at --svs-per-gpu times this budget so

@@ -47,11 +47,15 @@ constexpr int kWarpsPerBlock = NMSV_WPB;   // independent warps per block (each 
 #define NMSV_WARPS_PER_SM 16
 #endif
 constexpr unsigned kFull = 0xffffffffu;
+#ifndef NMSV_SAMPLE_STRIDE
+#define NMSV_SAMPLE_STRIDE 8       // the running maximum looks at every 8th row of a column (track()); measured on the
+                                   // bench batch: stride 4 221.2 ms, 8 217.0 ms, 16 219.5 ms (fewer DPX vs more false alarms)
+#endif
 constexpr int kSnapWords = 2 * (32 / 4 + 1);   // per lane and half: up to 32 rows as uint4 + one word (maximum before, step)
 constexpr int kMaxR = 32;          // largest strip height of any instantiation (head-room formula below)
 
 // a: constant part of the bias
-__host__ __device__ constexpr int sw_bias(int open, int ext) { return open + ext; }
+__host__ __device__ constexpr int sw_bias(int open, int ext) { return open + (NMSV_SAMPLE_STRIDE > 4 ? NMSV_SAMPLE_STRIDE - 3 : 1) * ext; }
 // 16-bit head-room a template needs on top of match * rows: the bias constant, one chunk of steps between two
 // rebases plus the 4-step unroll, and the row part of the bias. The host rejects longer templates (NMSV_E_RANGE).
 __host__ __device__ constexpr int sw_headroom(int open, int ext) { return sw_bias(open, ext) + ext + (kChunk + 4 + kMaxR) * ext; }
@@ -387,10 +391,7 @@ sw_wavefront_kernel(const SwParams p)
             // Filter threshold for TWO consecutive columns at once: an unsampled row lies at most stride-1 rows above a
             // sampled one and exceeds its H by at most open + (stride-2)*ext; the older column is compared at the newer
             // column's bias, i.e. one ext too strictly, hence open + (stride-1)*ext.
-#ifndef NMSV_SAMPLE_STRIDE
-#define NMSV_SAMPLE_STRIDE 4
-#endif
-            static_assert(NMSV_SAMPLE_STRIDE >= 2 && NMSV_SAMPLE_STRIDE <= 4, "the threshold must stay non-negative: a + 2*ext >= margin");
+            static_assert(NMSV_SAMPLE_STRIDE >= 2, "the threshold must stay non-negative: sw_bias + 2*ext >= margin");
             const uint32_t MARGIN2 = (uint32_t)((p.open + (NMSV_SAMPLE_STRIDE - 1) * ext) * 65537);
             // One column. tq = t - U is a multiple of 4, so every ring index of step t is a base computed once per four
             // steps plus the compile-time constant U (no per-step uniform-datapath arithmetic).
