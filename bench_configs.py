@@ -31,6 +31,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--only", default=None, help="comma-separated subset of the configurations")
     args = ap.parse_args()
 
     import torch
@@ -53,7 +54,10 @@ def main():
     plans = [("testdata_shaped", dict(n_sv=60)), ("colo829_shaped", dict(n_sv=40, contig_len=2_000_000, n_contigs=2)),
              ("insertion_heavy", dict(n_sv=24, contig_len=2_000_000, n_contigs=2)),
              ("single_breakend", dict(n_sv=300, contig_len=2_000_000, n_contigs=2))]
+    only = set(args.only.split(",")) if args.only else None
     for name, kw in plans:
+        if only and name not in only:
+            continue
         cfg = dataclasses.replace(synth.PRESETS[name], **kw)
         t0 = time.time()
         wl = synth.make_workload(cfg)
@@ -80,6 +84,10 @@ def main():
         print(json.dumps(entry), flush=True)
         results.append(entry)
 
+    if only and "pair_sweep" not in only:
+        if args.out:
+            json.dump({"device": eng.device_info(), "results": results}, open(args.out, "w"), indent=1)
+        return
     # config 5: the pair API (ssw_check semantics: both strands + begin pass)
     seqs, t_idx, r_idx = synth.make_pair_sweep(20000, m=400, n_min=1000, n_max=50000, pool_reads=4000, seed=5)
     pack = SeqPack()
@@ -95,8 +103,7 @@ def main():
     results.append(entry)
 
     if args.out:
-        info = eng.device_info() if hasattr(eng, "device_info") else {}
-        json.dump({"device": info, "results": results}, open(args.out, "w"), indent=1)
+        json.dump({"device": eng.device_info(), "results": results}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":

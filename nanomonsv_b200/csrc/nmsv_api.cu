@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -35,13 +36,20 @@ static const int kNumClasses = (int)(sizeof(kClassR) / sizeof(kClassR[0]));
 
 static int choose_class(uint32_t len)
 {
-    // fewest padded rows; ties -> taller strips (fewer tiles, fewer boundary round trips)
+    // Cheapest strip height for a template of `len` rows. One warp-step of the kernel costs about 8.25 * R issue cycles
+    // of DPX work (66 DPX per 16 rows, 2 cycles each) plus ~34 cycles that do not depend on R (shuffles, profile and
+    // ring loads, floor chain, loop), and a task runs tiles(len, R) * (columns + 31) steps: padded rows are paid for,
+    // but so are short strips. Ties -> taller strips (fewer boundary round trips).
+    if (const char* e = getenv("NMSV_FORCE_R")) {      // measurement knob
+        const int r = atoi(e);
+        for (int c = 0; c < kNumClasses; ++c) if (kClassR[c] == r) return c;
+    }
     int best = -1;
-    uint64_t best_rows = ~0ull;
+    double best_cost = 0.0;
     for (int c = 0; c < kNumClasses; ++c) {
-        uint64_t tile = 32ull * kClassR[c];
-        uint64_t rows = (len + tile - 1) / tile * tile;
-        if (rows <= best_rows) { best_rows = rows; best = c; }
+        const uint64_t tile = 32ull * kClassR[c];
+        const double cost = (double)((len + tile - 1) / tile) * (8.25 * kClassR[c] + 34.0);
+        if (best < 0 || cost <= best_cost) { best_cost = cost; best = c; }
     }
     return best;
 }
