@@ -8,6 +8,7 @@
 //   sw_wavefront_kernel  per strip class R on the reversed, bounded windows: begin cells  (parasail src/ssw.c)
 //   final_kernel         1-based 6-tuples (:153-162), final supporting decision, per-SV atomic counts, records
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -40,10 +41,9 @@ static int choose_class(uint32_t len)
     // of DPX work (66 DPX per 16 rows, 2 cycles each) plus ~34 cycles that do not depend on R (shuffles, profile and
     // ring loads, floor chain, loop), and a task runs tiles(len, R) * (columns + 31) steps: padded rows are paid for,
     // but so are short strips. Ties -> taller strips (fewer boundary round trips).
-    if (const char* e = getenv("NMSV_FORCE_R")) {      // measurement knob
-        const int r = atoi(e);
-        for (int c = 0; c < kNumClasses; ++c) if (kClassR[c] == r) return c;
-    }
+    static const int forced = [] { const char* e = getenv("NMSV_FORCE_R"); return e ? atoi(e) : 0; }();   // measurement knob
+    if (forced)
+        for (int c = 0; c < kNumClasses; ++c) if (kClassR[c] == forced) return c;
     int best = -1;
     double best_cost = 0.0;
     for (int c = 0; c < kNumClasses; ++c) {
@@ -686,21 +686,29 @@ static int check_template(nmsv_ctx* ctx, uint32_t idx, const uint32_t* lens, uin
     return NMSV_OK;
 }
 
-static int upload_seq_tables(nmsv_ctx* ctx, SeqTables& st, const uint8_t* codes, uint64_t n_codes,
-                             const uint64_t* offsets, const uint32_t* lens, uint32_t n_seqs)
+// The sequence bytes are by far the largest upload: it is issued first, so that the DMA runs while the host validates
+// the SV / read tables and sorts the reads; the strip classes (a result of that host work) follow in a second call.
+static int upload_seq_codes(nmsv_ctx* ctx, SeqTables& st, const uint8_t* codes, uint64_t n_codes,
+                            const uint64_t* offsets, const uint32_t* lens, uint32_t n_seqs)
 {
     cudaStream_t s = ctx->stream;
     CUDA_TRY(ctx, st.codes.alloc(n_codes, s));
     CUDA_TRY(ctx, st.offsets.alloc(sizeof(uint64_t) * n_seqs, s));
     CUDA_TRY(ctx, st.lens.alloc(sizeof(uint32_t) * n_seqs, s));
-    CUDA_TRY(ctx, st.seq_class.alloc(n_seqs, s));
     if (n_codes) CUDA_TRY(ctx, cudaMemcpyAsync(st.codes.p, codes, n_codes, cudaMemcpyHostToDevice, s));
     if (n_seqs) {
         CUDA_TRY(ctx, cudaMemcpyAsync(st.offsets.p, offsets, sizeof(uint64_t) * n_seqs, cudaMemcpyHostToDevice, s));
         CUDA_TRY(ctx, cudaMemcpyAsync(st.lens.p, lens, sizeof(uint32_t) * n_seqs, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(ctx, cudaMemcpyAsync(st.seq_class.p, st.cls_host.data(), n_seqs, cudaMemcpyHostToDevice, s));
     }
     st.h2d = n_codes + (uint64_t)n_seqs * (8 + 4 + 1);
+    return NMSV_OK;
+}
+
+static int upload_seq_classes(nmsv_ctx* ctx, SeqTables& st, uint32_t n_seqs)
+{
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(ctx, st.seq_class.alloc(n_seqs, s));
+    if (n_seqs) CUDA_TRY(ctx, cudaMemcpyAsync(st.seq_class.p, st.cls_host.data(), n_seqs, cudaMemcpyHostToDevice, s));
     return NMSV_OK;
 }
 
@@ -777,7 +785,11 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
     nmsv_plan* pl = new (std::nothrow) nmsv_plan();
     if (!pl) return set_err(ctx, NMSV_E_INVALID, "out of host memory");
     pl->ctx = ctx; pl->n_seqs = n_seqs; pl->n_svs = n_svs; pl->n_reads = n_reads; pl->sc = *scoring;
-    struct Guard { nmsv_plan* p; ~Guard() { if (p) nmsv_plan_destroy(p); } } guard{pl};
+    // on an error return the upload from the caller's buffers may still be in flight: wait for it before they go away
+    struct Guard { nmsv_plan* p; ~Guard() { if (p) { cudaStreamSynchronize(p->ctx->stream); nmsv_plan_destroy(p); } } } guard{pl};
+
+    rc = upload_seq_codes(ctx, pl->st, codes, n_codes, offsets, lens, n_seqs);      // DMA in flight during the host work below
+    if (rc) return rc;
 
     // ---- validate SVs, pick strip classes
     pl->st.cls_host.assign(n_seqs, 0);
@@ -846,7 +858,7 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
 
     // ---- upload
     cudaStream_t s = ctx->stream;
-    rc = upload_seq_tables(ctx, pl->st, codes, n_codes, offsets, lens, n_seqs);
+    rc = upload_seq_classes(ctx, pl->st, n_seqs);
     if (rc) return rc;
     CUDA_TRY(ctx, pl->svs.alloc(sizeof(nmsv_sv) * n_svs, s));
     CUDA_TRY(ctx, pl->reads.alloc(sizeof(nmsv_read) * n_reads, s));
@@ -1086,12 +1098,21 @@ extern "C" int nmsv_validate_batch(nmsv_ctx* ctx, const uint8_t* codes, uint64_t
                                    int32_t* checked, int32_t* supporting, nmsv_record* records,
                                    uint64_t record_capacity, uint64_t* n_records)
 {
+    static const bool trace = getenv("NMSV_TRACE") != nullptr;      // host-side phase times on stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0.0;
     nmsv_plan* pl = nullptr;
     int rc = nmsv_plan_create(ctx, &pl, codes, n_codes, offsets, lens, n_seqs, svs, n_svs, reads, n_reads, scoring);
     if (rc) return rc;
+    const double t1 = trace ? now() : 0.0;
     rc = nmsv_plan_run(pl);
+    const double t2 = trace ? now() : 0.0;
     if (!rc) rc = nmsv_plan_download(pl, checked, supporting, records, record_capacity, n_records);
+    const double t3 = trace ? now() : 0.0;
     nmsv_plan_destroy(pl);
+    if (trace)
+        fprintf(stderr, "[nmsv] validate_batch: create+upload %.2f ms, launch %.2f ms, wait+download %.2f ms, destroy %.2f ms\n",
+                t1 - t0, t2 - t1, t3 - t2, now() - t3);
     return rc;
 }
 
@@ -1115,6 +1136,10 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 
     SeqTables st;
+    // the sequence upload runs while the host checks the pairs; an error return waits for it (the caller's buffers)
+    struct InFlight { cudaStream_t s; bool armed; ~InFlight() { if (armed) cudaStreamSynchronize(s); } } in_flight{ctx->stream, true};
+    rc = upload_seq_codes(ctx, st, codes, n_codes, offsets, lens, n_seqs);
+    if (rc) return rc;
     st.cls_host.assign(n_seqs, 0);
     bool class_used[8] = {false};
     uint32_t max_cols_multi = 0;
@@ -1136,7 +1161,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     for (int c = 0; c < kNumClasses; ++c) if (class_used[c]) classes.push_back(c);
 
     cudaStream_t s = ctx->stream;
-    rc = upload_seq_tables(ctx, st, codes, n_codes, offsets, lens, n_seqs);
+    rc = upload_seq_classes(ctx, st, n_seqs);
     if (rc) return rc;
     DevBuf d_t, d_rc, d_r, tasks, fwd, rev_tasks, rev_ready, rev, sel, counters, bnd, d_out;
     CUDA_TRY(ctx, d_t.alloc(4ull * n_pairs, s));
