@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import ALN_DTYPE, READ_DTYPE, RECORD_DTYPE, SSW_RESULT_DTYPE, SV_DTYPE, Scoring, Stats
-from .my_seq import CODE_LUT
+from .my_seq import encode as _encode
 
 
 class EngineError(RuntimeError):
@@ -47,7 +47,7 @@ class SeqPack:
             hit = self._seen.get(seq)
             if hit is not None:
                 return hit
-        idx = self.add_codes(CODE_LUT[np.frombuffer(seq.encode("latin-1"), dtype=np.uint8)])
+        idx = self.add_codes(_encode(seq))
         if self._dedup:
             self._seen[seq] = idx
         return idx
