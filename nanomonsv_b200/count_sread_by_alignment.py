@@ -24,6 +24,7 @@ import os
 import random
 import subprocess
 from dataclasses import dataclass, field
+from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -265,6 +266,8 @@ class Alignment_counter(object):
         self._queue: List[SvJob] = []
         self._queued_bases = 0
         self.batches_run = 0
+        self._pool: Optional[ThreadPoolExecutor] = None
+        self._pending = None            # (future, jobs, sv table) of the batch that is on the GPU
 
     # ---- reference-shaped interface
     def initialize(self, key, is_sbnd=False):
@@ -305,10 +308,15 @@ class Alignment_counter(object):
         self._queued_bases += self._job.bases
         self._job = None
         if self._queued_bases >= BATCH_BASES:
-            self.flush()
+            self._submit()
 
     # ---- GPU batch
     def flush(self):
+        """Send what is queued to the GPU and write every pending count / info line."""
+        self._submit()
+        self._drain()
+
+    def _submit(self):
         if not self._queue:
             return
         eng = self._engine or default_engine()
@@ -320,13 +328,27 @@ class Alignment_counter(object):
                 m1, m2 = job.read_mapq.get(rid, (None, None))
                 bb.add_read(job.read_seqs[rid], m1, m2)
         pack, svs, reads = bb.finalize()
-        checked, supporting, records = eng.validate(pack, svs, reads, self.scoring)
+        # The GPU call runs on a worker thread (ctypes releases the GIL), so the caller goes on parsing and encoding the
+        # next batch meanwhile; results are written strictly in submission order (at the next flush, or at close()).
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=1)
+        fut = self._pool.submit(eng.validate, pack, svs, reads, self.scoring)
+        queue, self._queue, self._queued_bases = self._queue, [], 0
+        self._drain()
+        self._pending = (fut, queue, svs)
         self.batches_run += 1
 
+    def _drain(self):
+        """Wait for the batch in flight (if any) and write its count / info lines."""
+        if self._pending is None:
+            return
+        fut, queue, svs = self._pending
+        self._pending = None
+        checked, supporting, records = fut.result()       # re-raises an EngineError of the worker
         by_sv: Dict[int, list] = {}
         for rec in records:
             by_sv.setdefault(int(rec["sv"]), []).append(rec)
-        for i, job in enumerate(self._queue):
+        for i, job in enumerate(queue):
             head = "\t".join(job.key.split(","))
             print(f"{head}\t{int(checked[i])}\t{int(supporting[i])}", file=self.hout_count)
             for rec in by_sv.get(i, []):
@@ -337,11 +359,12 @@ class Alignment_counter(object):
                     fields = _aln_list(rec["aln"][0]) + _aln_list(rec["aln"][1])
                     fields += (_aln_list(rec["aln"][2]) + _aln_list(rec["aln"][3])) if job.short else ["None"] * 12
                 print(f"{head}\t{rid}\t" + "\t".join(str(x) for x in fields), file=self.hout_ainfo)
-        self._queue = []
-        self._queued_bases = 0
 
     def close(self):
         self.flush()
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
         for h in (self.hout_count, self.hout_ainfo):
             if not h.closed:
                 h.close()
