@@ -351,14 +351,15 @@ def main():
         h2d = st["h2d_bytes"]
         roofline = {
             "bound": "int_alu (DPX issue rate; not hbm, not tensor)",
-            "kernel": f"sw_wavefront_kernel<{dom_r}> (forward pass)",
+            "kernel": f"sw_wavefront_kernel<{dom_r}> (forward launch; it also drains the fused begin pass, whose cells are not counted)",
             "achieved": achieved / 1e12, "peak": dpx_peak / 1e12, "unit": "T DPX lane-inst/s",
             "frac": achieved / dpx_peak,
             "peak_source": "measured live: register-only VIADDMNMX.S16x2 loop on this GPU (nmsv_measure_dpx_peak)",
             "dpx_lane_inst_per_cell": DPX_PER_CELL,
             "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / step_kernel_ms,
             "gcups_kernel": st["cells_executed"] / (dom_ms * 1e-3) / 1e9,
-            "traffic": _traffic(st["cells_executed"]),
+            "traffic": _traffic(st["cells_executed"])[0],            # DRAM bytes per launch (ncu), or null
+            "traffic_source": _traffic(st["cells_executed"])[1],
             "hbm": {"algorithmic_bytes": int(codes.size), "achieved_gbs": codes.size / (dom_ms * 1e-3) / 1e9,
                     "peak_gbs": _measured_peaks().get("hbm_gbs"), "note": "HBM is 3-4 orders of magnitude off the critical path"},
             "launches_ms": [{"kernel": n, "R": r, "ms": round(ms, 4)} for n, r, ms in ktimes],
@@ -407,10 +408,9 @@ def _traffic(cells_executed: float):
     (the traffic is the per-column tile-boundary spill, proportional to the cells). None if the capture is absent."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
-        return {"dram_bytes_per_launch": t["dram_bytes_per_executed_cell"] * cells_executed,
-                "source": t["source"] + ", scaled by executed cells"}
+        return t["dram_bytes_per_executed_cell"] * cells_executed, t["source"] + ", scaled by executed cells"
     except Exception:   # noqa: BLE001
-        return None
+        return None, None
 
 
 def _measured_peaks() -> dict:
