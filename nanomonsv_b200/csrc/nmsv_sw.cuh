@@ -22,7 +22,7 @@
 //         H  = VIMNMX3.S16x2  (x, FL, F)                   max(x, F, 0)
 //         E' = VIADDMNMX.S16x2(H, ext - open, E)           max(H - open, E - ext)
 //         F' = VIADDMNMX.S16x2(H, ext - open, F)           max(H - open, F - ext)
-//     plus 1 DPX per 8 cells for the sampled running maximum. a = open + ext (sw_bias) keeps the low half of every
+//     plus 1 DPX per 16 cells for the sampled running maximum. a (sw_bias) keeps the low half of every
 //     value that is touched by a plain 32-bit add non-negative, so no borrow crosses the halves; the bias is
 //     rebased at chunk boundaries before 16 bits could overflow.
 #pragma once
@@ -52,13 +52,21 @@ constexpr unsigned kFull = 0xffffffffu;
                                    // bench batch: stride 4 221.2 ms, 8 217.0 ms, 16 219.5 ms (fewer DPX vs more false alarms)
 #endif
 constexpr int kSnapWords = 2 * (32 / 4 + 1);   // per lane and half: up to 32 rows as uint4 + one word (maximum before, step)
+#ifndef NMSV_UNROLL
+#define NMSV_UNROLL 8
+#endif
+constexpr int kUnroll = NMSV_UNROLL;       // steps per iteration of the inner loop; measured 4 / 8 / 16: 217.1 / 210.1 ms /
+                                           // register-bound (the floor window and the ring indices are shared by more steps)
+static_assert(kUnroll == 4 || kUnroll == 8 || kUnroll == 16, "the 32-step groups are cut into kUnroll-step bodies");
 constexpr int kMaxR = 32;          // largest strip height of any instantiation (head-room formula below)
 
 // a: constant part of the bias
-__host__ __device__ constexpr int sw_bias(int open, int ext) { return open + (NMSV_SAMPLE_STRIDE > 4 ? NMSV_SAMPLE_STRIDE - 3 : 1) * ext; }
+// (+1: the warp-wide lift subtracts 1 from a running maximum, which is never below a; the margin term keeps the
+// carried threshold = maximum - margin non-negative from the first step on)
+__host__ __device__ constexpr int sw_bias(int open, int ext) { return open + (NMSV_SAMPLE_STRIDE > 2 ? NMSV_SAMPLE_STRIDE - 1 : 1) * ext + 1; }
 // 16-bit head-room a template needs on top of match * rows: the bias constant, one chunk of steps between two
 // rebases plus the 4-step unroll, and the row part of the bias. The host rejects longer templates (NMSV_E_RANGE).
-__host__ __device__ constexpr int sw_headroom(int open, int ext) { return sw_bias(open, ext) + ext + (kChunk + 4 + kMaxR) * ext; }
+__host__ __device__ constexpr int sw_headroom(int open, int ext) { return sw_bias(open, ext) + ext + (kChunk + kUnroll + kMaxR) * ext; }
 
 enum : uint32_t { kARev = 1u, kAComp = 2u, kBRev = 4u, kBComp = 8u, kCRev = 16u };
 
@@ -328,9 +336,9 @@ sw_wavefront_kernel(const SwParams p)
         const bool c_rev = task.flags & kCRev;
         const int rows = a_len > b_len ? a_len : b_len;
         const int ntiles = (rows + 32 * R - 1) / (32 * R);
-        const int total_steps = (ncols + 31 + 3) & ~3;   // multiple of 4: the step body is unrolled 4x (pad steps are inert)
+        const int total_steps = (ncols + 31 + kUnroll - 1) & ~(kUnroll - 1);   // the step body is unrolled kUnroll x (pad steps are inert)
         // steps the bias may run before the 16-bit lanes could overflow (host guarantees >= kChunk)
-        const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext - kMaxR - 4 : 0x7fffffff;
+        const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext - kMaxR - kUnroll : 0x7fffffff;
 
         // running best over tiles, per half: {score, col, row}
         int bs0 = 0, bc0 = 0, br0 = a_len - 1;
@@ -372,13 +380,18 @@ sw_wavefront_kernel(const SwParams p)
                 }
             }
 
-            // H of the previous column ping-pongs between HA and HB over a 2-step unrolled body, so that no
-            // register moves are needed to keep Hdiag alive while the new column is written.
+            // H of the previous column ping-pongs between HA and HB over the unrolled body, so that no register moves
+            // are needed to keep Hdiag alive while the new column is written.
             uint32_t HA[R], HB[R], E[R];
 #pragma unroll
             for (int k = 0; k < R; ++k) {       // zero state with the bias of "after step -1": row k carries k*ext
                 HA[k] = FLOOR0 + (uint32_t)k * p.ext2; HB[k] = HA[k]; E[k] = EF0 + (uint32_t)(k + 1) * p.ext2;
             }
+            // Filter threshold for TWO consecutive columns at once: an unsampled row lies at most stride-1 rows above a
+            // sampled one and exceeds its H by at most open + (stride-2)*ext; the older column is compared at the newer
+            // column's bias, i.e. one ext too strictly, hence open + (stride-1)*ext.
+            static_assert(NMSV_SAMPLE_STRIDE >= 2, "the threshold must stay non-negative: sw_bias + 2*ext >= margin");
+            const uint32_t MARGIN2 = (uint32_t)((p.open + (NMSV_SAMPLE_STRIDE - 1) * ext) * 65537);
             // later tiles start their running maximum at (best of the earlier tiles - 1), per half
             uint32_t bestprev = FLOOR0 + pack16(bs0 > 0 ? bs0 - 1 : 0, bs1 > 0 ? bs1 - 1 : 0);
             uint32_t flb = FLOOR0 + p.ext2;     // floor of row k at step t is flb + (t+k)*ext2 = FLOOR0 + (t - tbase + k)*ext2
@@ -388,14 +401,9 @@ sw_wavefront_kernel(const SwParams p)
             // prefetched is a pure function of t0 (a mutable flag would cost the compiler its uniformity analysis)
             const bool tma_task = !c_rev && ((task.c_base & 15ull) == 0);
 
-            // Filter threshold for TWO consecutive columns at once: an unsampled row lies at most stride-1 rows above a
-            // sampled one and exceeds its H by at most open + (stride-2)*ext; the older column is compared at the newer
-            // column's bias, i.e. one ext too strictly, hence open + (stride-1)*ext.
-            static_assert(NMSV_SAMPLE_STRIDE >= 2, "the threshold must stay non-negative: sw_bias + 2*ext >= margin");
-            const uint32_t MARGIN2 = (uint32_t)((p.open + (NMSV_SAMPLE_STRIDE - 1) * ext) * 65537);
             // One column. tq = t - U is a multiple of 4, so every ring index of step t is a base computed once per four
             // steps plus the compile-time constant U (no per-step uniform-datapath arithmetic).
-            auto column = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const uint32_t (&FL)[R + 3], const char* bq,
+            auto column = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const uint32_t (&FL)[R + kUnroll - 1], const char* bq,
                               const uint8_t* rq, uint2* sq, const int U) {
                 const uint32_t sh = __shfl_up_sync(kFull, h_last, 1);
                 const uint32_t sf = __shfl_up_sync(kFull, f_out, 1);
@@ -404,8 +412,8 @@ sw_wavefront_kernel(const SwParams p)
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hin) : "r"(sh), "r"(m1), "r"(bv.x));
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(fin) : "r"(sf), "r"(m1), "r"(bv.y));
                 const uint32_t b = rq[U];
-                const uint4* pp = prof + b * (G * 32) + lane;
                 uint32_t S[4 * G];
+                const uint4* pp = prof + b * (G * 32) + lane;
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
                     const uint4 v = pp[g * 32];
@@ -462,7 +470,7 @@ sw_wavefront_kernel(const SwParams p)
             };
             auto track = [&](const uint32_t (&Ha)[R], const uint32_t (&Hb)[R], const int t) {
                 const uint32_t bp2 = add_halves(bestprev, 2 * ext);      // running maximum at the newer step's row-0 bias
-                const uint32_t thr = bp2 - MARGIN2;                       // bp2 >= a + 2*ext = open + 3*ext in both halves: no borrow
+                const uint32_t thr = bp2 - MARGIN2;                       // bp2 >= a + 2*ext >= margin in both halves: no borrow
                 uint32_t q = thr;
 #pragma unroll
                 for (int k = R - 1; k >= 0; k -= NMSV_SAMPLE_STRIDE) {
@@ -555,21 +563,21 @@ sw_wavefront_kernel(const SwParams p)
                 const int t1 = (t0 + kChunk < total_steps) ? t0 + kChunk : total_steps;
                 for (int g0 = t0; g0 < t1; g0 += 32) {
                     const int g1 = (g0 + 32 < t1) ? g0 + 32 : t1;     // g1 - g0 is even (total_steps is even)
-                    for (int t = g0; t < g1; t += 4) {        // g0, g1 and total_steps are multiples of 4
-                        uint32_t FL[R + 3];      // floors of (step t+u, row k) = FL[u + k]: warp-uniform sliding window
+                    for (int t = g0; t < g1; t += kUnroll) {        // g0, g1 and total_steps are multiples of kUnroll
+                        uint32_t FL[R + kUnroll - 1];      // floors of (step t+u, row k) = FL[u + k]: warp-uniform sliding window
                         FL[0] = flb + (uint32_t)t * p.ext2;
 #pragma unroll
-                        for (int i = 1; i < R + 3; ++i)      // IMAD chain, FMA pipe
+                        for (int i = 1; i < R + kUnroll - 1; ++i)      // IMAD chain, FMA pipe
                             asm("mad.lo.u32 %0, %1, 65537, %2;" : "=r"(FL[i]) : "r"(ext_v), "r"(FL[i - 1]));
                         const char* bq = bsrc + (uint32_t)(t & (kChunk - 1)) * bstride;
                         const uint8_t* rq = rlane + (t & (kRing - 1));
                         uint2* sq = bstage + (t & 31);
-                        column(HA, HB, FL, bq, rq, sq, 0);
-                        column(HB, HA, FL, bq, rq, sq, 1);
-                        track(HB, HA, t);
-                        column(HA, HB, FL, bq, rq, sq, 2);
-                        column(HB, HA, FL, bq, rq, sq, 3);
-                        track(HB, HA, t + 2);
+#pragma unroll
+                        for (int u = 0; u < kUnroll; u += 2) {      // fully unrolled: u is a constant in every copy
+                            column(HA, HB, FL, bq, rq, sq, u);
+                            column(HB, HA, FL, bq, rq, sq, u + 1);
+                            track(HB, HA, t + u);
+                        }
                     }
                     // ---- event filter: only a cell that reaches the final maximum of the whole alignment matters, and
                     //      any H seen so far is a lower bound of it. Lift every lane's running maximum to (warp-wide

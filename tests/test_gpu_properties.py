@@ -158,9 +158,9 @@ def test_longest_accepted_template_is_exact(engine):
     still be exact; one base more must be refused, for every strip height."""
     from nanomonsv_b200.engine import EngineError
     rng = np.random.default_rng(17)
-    # match * len + headroom <= 32767 - match - 1 with headroom (nmsv_sw.cuh: sw_headroom) = bias (open + 5 * ext)
-    # + ext + (128 + 4 + 32) * ext = 173
-    lmax = (32767 - 2 - 1 - 173) // 2
+    # match * len + headroom <= 32767 - match - 1 with headroom (nmsv_sw.cuh: sw_headroom) = bias (open + 7 * ext + 1)
+    # + ext + (128 + 8 + 32) * ext = 180
+    lmax = (32767 - 2 - 1 - 180) // 2
     tmpl = _rand(rng, lmax)
     body = np.concatenate((_rand(rng, 700), tmpl, _rand(rng, 900)))
     pack = SeqPack()
