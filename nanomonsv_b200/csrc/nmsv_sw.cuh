@@ -377,7 +377,6 @@ sw_wavefront_kernel(const SwParams p)
                 if (lane == 0) {      // bias change from (step t-1, row R-1 / R) of the lane above to (step t, row -1 / 0)
                     const uint32_t lift = (uint32_t)(-((R - 1) * ext * 65537));
                     bconst[0] = make_uint2(lift, lift);
-                    bconst[1] = make_uint2(lift, lift);     // (16-byte loads of the slot, NMSV_PAIR_IO)
                 }
             }
 
@@ -404,21 +403,11 @@ sw_wavefront_kernel(const SwParams p)
 
             // One column. tq = t - U is a multiple of 4, so every ring index of step t is a base computed once per four
             // steps plus the compile-time constant U (no per-step uniform-datapath arithmetic).
-#ifdef NMSV_PAIR_IO
-            uint4 bv2 = make_uint4(0u, 0u, 0u, 0u);
-            uint32_t stg_h = 0, stg_f = 0;
-#endif
             auto column = [&](const uint32_t (&Hs)[R], uint32_t (&Hd)[R], const uint32_t (&FL)[R + kUnroll - 1], const char* bq,
                               const uint8_t* rq, uint2* sq, const int U) {
                 const uint32_t sh = __shfl_up_sync(kFull, h_last, 1);
                 const uint32_t sf = __shfl_up_sync(kFull, f_out, 1);
-#ifdef NMSV_PAIR_IO
-                // boundary inputs of two steps with one 16-byte load (even U), staged outputs with one 16-byte store (odd U)
-                if ((U & 1) == 0) bv2 = *reinterpret_cast<const uint4*>(bq + (uint32_t)U * bstride);
-                const uint2 bv = (U & 1) ? make_uint2(bv2.z, bv2.w) : make_uint2(bv2.x, bv2.y);
-#else
                 const uint2 bv = *reinterpret_cast<const uint2*>(bq + (uint32_t)U * bstride);
-#endif
                 uint32_t hin, fin;     // H / F of the row above this strip, lifted to this step's bias
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hin) : "r"(sh), "r"(m1), "r"(bv.x));
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(fin) : "r"(sf), "r"(m1), "r"(bv.y));
@@ -442,12 +431,7 @@ sw_wavefront_kernel(const SwParams p)
                 diag = hin;
                 h_last = Hd[R - 1];
                 f_out = F;
-#ifdef NMSV_PAIR_IO
-                if ((U & 1) == 0) { stg_h = h_last; stg_f = f_out; }
-                else if (stage_lane) *reinterpret_cast<uint4*>(sq + (U - 1)) = make_uint4(stg_h, stg_f, h_last, f_out);
-#else
                 if (stage_lane) sq[U] = make_uint2(h_last, f_out);
-#endif
             };
             // ---- running maximum after a pair of columns (older column in Ha, newer in Hb; t = step of the older).
             // Rows k and k' <= k of one column satisfy H[k] >= H[k'] - open - (k-k'-1)*ext (through F), so if no row
