@@ -13,6 +13,11 @@ What is restated here (reference = /root/reference, nanomonsv v0.8.0):
   * Alignment_counter.initialize / generate_segment_fasta_files[_sbnd] / count_alignment_and_print[_sbnd]
                                                        (count_sread_by_alignment.py:207-397)
   * the streaming group-by of count_sread_by_alignment (count_sread_by_alignment.py:414-448)
+
+Pins: the host-logic restatements above (everything but the parasail.ssw arithmetic) are PINNED on a run of the
+reference's own count_sread_by_alignment (tests/golden/stage_reference.json, made by tests/golden/make_golden_stage.py
+with stand-in pysam / parasail modules; checked by tests/test_stage_reference.py). The arithmetic is pinned on the
+hand-derived and machine-made vectors under tests/golden/ only: PARITY UNPINNED against a real parasail binary.
 """
 from __future__ import annotations
 
