@@ -65,7 +65,7 @@ constexpr int kMaxR = 32;          // largest strip height of any instantiation 
 // carried threshold = maximum - margin non-negative from the first step on)
 __host__ __device__ constexpr int sw_bias(int open, int ext) { return open + (NMSV_SAMPLE_STRIDE > 2 ? NMSV_SAMPLE_STRIDE - 1 : 1) * ext + 1; }
 // 16-bit head-room a template needs on top of match * rows: the bias constant, one chunk of steps between two
-// rebases plus the 4-step unroll, and the row part of the bias. The host rejects longer templates (NMSV_E_RANGE).
+// rebases plus the unrolled body, and the row part of the bias. The host rejects longer templates (NMSV_E_RANGE).
 __host__ __device__ constexpr int sw_headroom(int open, int ext) { return sw_bias(open, ext) + ext + (kChunk + kUnroll + kMaxR) * ext; }
 
 enum : uint32_t { kARev = 1u, kAComp = 2u, kBRev = 4u, kBComp = 8u, kCRev = 16u };
@@ -261,7 +261,7 @@ __device__ __noinline__ void sw_task_done(const GroupHook* hook, uint32_t* group
 
 // OPEN/EXT >= 0: gap penalties known at compile time (the reference always calls parasail.ssw(.., 3, 1, ..),
 // count_sread_by_alignment.py:148): the DPX add operands become immediates, which saves one vector-register read on
-// two of the 4.5 DPX instructions per cell pair. OPEN = EXT = -1: generic instantiation, operands from the parameters.
+// two of the four DPX instructions per cell pair. OPEN = EXT = -1: generic instantiation, operands from the parameters.
 template <int R, int OPEN, int EXT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, ((R <= 16 ? NMSV_WARPS_PER_SM : (R <= 19 ? 12 : 8)) / kWarpsPerBlock > 0 ? (R <= 16 ? NMSV_WARPS_PER_SM : (R <= 19 ? 12 : 8)) / kWarpsPerBlock : 1))
 sw_wavefront_kernel(const SwParams p)
@@ -282,10 +282,11 @@ sw_wavefront_kernel(const SwParams p)
     uint4* const snap_lane = p.snap + (size_t)gwarp * (kSnapWords * 32) + lane;    // word w of half h: [(h * (G+1) + w) * 32]
 
     const uint32_t n_tasks = p.n_tasks_dev ? *p.n_tasks_dev : p.n_tasks;
-    // Every stored H/E/F value is  true value + a + beta_t  with a = open + ext and beta_t = (t - tbase) * ext:
-    //   * a keeps E - ext and F - ext non-negative in the low half, so they are plain 32-bit adds (FMA pipe);
-    //   * beta grows by ext per step, which turns  E' = max(H - open, E - ext)  into  max(H + (ext - open), E):
-    //     the horizontal gap extension costs no instruction at all. beta is rebased at chunk boundaries.
+    // Every stored H/E/F value of (step t, strip row k) is  true value + a + (t - tbase + k) * ext  (header comment):
+    //   * the bias grows by ext per step AND per row, which turns  E' = max(H - open, E - ext)  and
+    //     F' = max(H - open, F - ext)  into  max(H + (ext - open), E / F): neither gap extension costs an instruction;
+    //   * a = sw_bias keeps the low half of everything that a plain 32-bit add touches non-negative (no borrow between
+    //     the halves); the step part is rebased at chunk boundaries.
     const int bias = sw_bias(p.open, p.ext);
     const uint32_t FLOOR0 = pack16(bias, bias);
     const uint32_t EF0 = pack16(bias - p.open, bias - p.open);          // E = F = -open
