@@ -151,6 +151,10 @@ int nmsv_measure_dpx_peak(nmsv_ctx *ctx, double *lane_inst_per_s);
 
 /* byte -> code with the mapper of parasail.matrix_create("ACGT", ...): case-insensitive ACGT, rest wildcard */
 void nmsv_encode_ascii(const char *ascii, uint64_t n, uint8_t *codes);
+/* the same mapper for many sequences that lie inside one ASCII buffer (a block of the seam TSV of
+ * count_sread_by_alignment.py:109-111): sequence i = src[src_off[i], +lens[i]) goes to dst[dst_off[i], ...); host only */
+void nmsv_encode_pack(const char *src, const uint64_t *src_off, const uint32_t *lens, const uint64_t *dst_off,
+                      uint64_t n_seqs, uint8_t *dst);
 
 /* ---- operator seam: batched parasail.ssw ---------------------------------------------------------------------- */
 int nmsv_ssw_batch(nmsv_ctx *ctx, const uint8_t *codes, uint64_t n_codes, const uint64_t *offsets,

@@ -58,7 +58,7 @@ class Stats(ctypes.Structure):
 
 
 EXPORTS = ["nmsv_abi_version", "nmsv_create", "nmsv_destroy", "nmsv_last_error", "nmsv_set_stream",
-           "nmsv_device_info", "nmsv_encode_ascii", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
+           "nmsv_device_info", "nmsv_encode_ascii", "nmsv_encode_pack", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
            "nmsv_plan_create", "nmsv_plan_run", "nmsv_plan_download", "nmsv_plan_stats", "nmsv_plan_download_alns",
            "nmsv_plan_destroy", "nmsv_plan_set_profiling", "nmsv_plan_kernel_times", "nmsv_plan_copy_counts_device",
            "nmsv_measure_dpx_peak", "nmsv_sw_jump_batch"]
@@ -102,6 +102,8 @@ def load() -> ctypes.CDLL:
     L.nmsv_device_info.restype = ctypes.c_int
     L.nmsv_encode_ascii.argtypes = [ctypes.c_char_p, u64, vp]
     L.nmsv_encode_ascii.restype = None
+    L.nmsv_encode_pack.argtypes = [vp, vp, vp, vp, u64, vp]
+    L.nmsv_encode_pack.restype = None
     sc = ctypes.POINTER(Scoring)
     L.nmsv_ssw_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, vp, u64, sc, ctypes.c_int, vp]
     L.nmsv_ssw_batch.restype = ctypes.c_int

@@ -8,7 +8,7 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from . import _lib
-from .engine import SeqPack
+from .engine import AsciiSlice, SeqPack
 from .my_seq import needs_explicit_revcomp, reverse_complement
 
 
@@ -69,7 +69,12 @@ class BatchBuilder:
 
     def add_read(self, seq: Union[str, np.ndarray], mapq1: Optional[int], mapq2: Optional[int]) -> int:
         assert self._open_sv is not None, "add_sv first"
-        idx = self.pack.add(seq) if isinstance(seq, str) else self.pack.add_codes(seq)
+        if isinstance(seq, str):
+            idx = self.pack.add(seq)
+        elif isinstance(seq, AsciiSlice):
+            idx = self.pack.add_ascii_slice(seq)
+        else:
+            idx = self.pack.add_codes(seq)
         self.bases += self.pack.length(idx)
         self._reads.append((idx, self._open_sv, _lib.MAPQ_NONE if mapq1 is None else int(mapq1),
                             _lib.MAPQ_NONE if mapq2 is None else int(mapq2)))

@@ -31,7 +31,7 @@ import numpy as np
 
 from . import _lib
 from .batch import BatchBuilder, integer_bounds  # noqa: F401
-from .engine import DEFAULT_SCORING, Engine, SeqPack, default_engine
+from .engine import DEFAULT_SCORING, AsciiSlice, Engine, SeqPack, default_engine
 from .my_seq import needs_explicit_revcomp, reverse_complement
 
 # maximum number of read bases packed into one device batch (host memory / H2D granularity, not a GPU limit)
@@ -295,6 +295,24 @@ class Alignment_counter(object):
         job.read_seqs[rid] = seq
         job.bases += len(seq)
 
+    def _add_encoded_read(self, rid_b: bytes, codes, mapq1_b: bytes, mapq2_b: Optional[bytes]):
+        """add_long_read_seq for the byte-level reader: fields as bytes; the sequence, already stripped, as a code array
+        or as an AsciiSlice of the block it was read in."""
+        job = self._job
+        tok = rid_b.decode().split()
+        rid = tok[0] if tok else ""
+        job.read_mapq[rid] = (None if mapq1_b == b"None" else int(mapq1_b),
+                              None if mapq2_b is None or mapq2_b == b"None" else int(mapq2_b))
+        n = len(codes)
+        if n == 0:
+            return
+        if rid not in job.read_seqs:
+            job.read_ids.append(rid)
+        else:
+            job.bases -= len(job.read_seqs[rid])
+        job.read_seqs[rid] = codes
+        job.bases += n
+
     def count_alignment_and_print(self):
         self._enqueue()
 
@@ -381,6 +399,64 @@ class Alignment_counter(object):
             pass
 
 
+SEAM_CHUNK_BYTES = int(os.environ.get("NMSV_SEAM_CHUNK", str(64 << 20)))
+_WS = b" \t\r\n\x0b\x0c"
+
+
+def _stream_seam_fast(seam_file: str, counter: Alignment_counter, is_sbnd: bool) -> None:
+    """The same group-by as _stream_seam, on bytes: the file is read in large blocks, the five fields of a line are
+    located with bytes.find (memchr), and every read reaches the batch as a slice of the block it was read in; the
+    library encodes and packs all of them in one pass when the batch is finalized (nmsv_encode_pack) -- no per-read
+    str objects, no per-read encoding, no intermediate copies. The line-by-line reader stays as the executable
+    specification (tests/test_abi_and_host.py holds the two to identical batches)."""
+    def close_group():
+        if counter.temp_key is not None:
+            counter.count_alignment_and_print_sbnd() if is_sbnd else counter.count_alignment_and_print()
+
+    cur_key = None                         # bytes of the key column of the open group
+    with open(seam_file, "rb") as hin:
+        rest = b""
+        while True:
+            block = hin.read(SEAM_CHUNK_BYTES)
+            data = rest + block
+            if block:
+                cut = data.rfind(b"\n") + 1
+                data, rest = data[:cut], data[cut:]        # whole lines now, the partial last line with the next block
+            else:
+                rest = b""
+                if data and not data.endswith(b"\n"):
+                    data += b"\n"
+            if data:
+                src = np.frombuffer(data, dtype=np.uint8)      # the reads stay ASCII in this block until the batch is packed
+                find = data.find
+                pos, n = 0, len(data)
+                while pos < n:
+                    le = find(b"\n", pos)
+                    t0 = find(b"\t", pos, le)
+                    t1 = find(b"\t", t0 + 1, le)
+                    t2 = find(b"\t", t1 + 1, le)
+                    t3 = find(b"\t", t2 + 1, le)
+                    if t0 < 0 or t1 < 0 or t2 < 0 or t3 < 0 or find(b"\t", t3 + 1, le) >= 0:
+                        raise ValueError(f"{seam_file}: a line does not have 5 tab-separated fields")
+                    kb = data[pos:t0]
+                    if kb != cur_key:
+                        close_group()
+                        counter.initialize(kb.decode(), is_sbnd=is_sbnd)
+                        cur_key = kb
+                    a, b = t3 + 1, le
+                    while b > a and data[b - 1] in _WS:          # str.strip() of the line-by-line reader (e.g. CR LF files)
+                        b -= 1
+                    while a < b and data[a] in _WS:
+                        a += 1
+                    counter._add_encoded_read(data[t0 + 1:t1], AsciiSlice(src, a, b - a), data[t1 + 1:t2],
+                                              None if is_sbnd else data[t2 + 1:t3])
+                    pos = le + 1
+            if not block:
+                break
+    close_group()
+    counter.close()
+
+
 def _stream_seam(seam_file: str, counter: Alignment_counter, is_sbnd: bool) -> None:
     """Group-by over the key-sorted seam TSV (reference :414-425 and :436-448)."""
     with open(seam_file) as hin:
@@ -403,7 +479,8 @@ def count_sread_from_seam(seam_file, output_count_file, output_alignment_info_fi
     """The part of count_sread_by_alignment after read gathering: seam TSV -> sread_count / sread_info files."""
     counter = Alignment_counter(output_count_file, output_alignment_info_file, reference_fasta, var_read_min_mapq,
                                 score_ratio_thres, False, debug, engine=engine, **kwargs)
-    _stream_seam(seam_file, counter, is_sbnd)
+    reader = kwargs_reader if (kwargs_reader := os.environ.get("NMSV_SEAM_READER")) else "bytes"
+    (_stream_seam if reader == "lines" else _stream_seam_fast)(seam_file, counter, is_sbnd)
     return counter
 
 

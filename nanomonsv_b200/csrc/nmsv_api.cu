@@ -243,6 +243,33 @@ extern "C" int nmsv_device_info(const nmsv_ctx* ctx, int32_t* sm_count, int32_t*
     return NMSV_OK;
 }
 
+static const uint8_t* code_table()
+{
+    static uint8_t tab[256];
+    static const bool init = [] {
+        for (int i = 0; i < 256; ++i) tab[i] = 4;
+        tab['A'] = tab['a'] = 0; tab['C'] = tab['c'] = 1; tab['G'] = tab['g'] = 2; tab['T'] = tab['t'] = 3;
+        return true;
+    }();
+    (void)init;
+    return tab;
+}
+
+// Host-side packing for callers that hold the reads as ASCII inside one large buffer (a seam TSV read or mapped in
+// blocks): sequence i = src[src_off[i] .. +lens[i]) is encoded straight to dst[dst_off[i] ..), one pass, no
+// intermediate copies. Bytes of dst between the sequences are left as they are (the caller pre-fills the padding).
+extern "C" void nmsv_encode_pack(const char* src, const uint64_t* src_off, const uint32_t* lens, const uint64_t* dst_off,
+                                 uint64_t n_seqs, uint8_t* dst)
+{
+    const uint8_t* tab = code_table();
+    for (uint64_t s = 0; s < n_seqs; ++s) {
+        const uint8_t* in = reinterpret_cast<const uint8_t*>(src) + src_off[s];
+        uint8_t* out = dst + dst_off[s];
+        const uint32_t n = lens[s];
+        for (uint32_t i = 0; i < n; ++i) out[i] = tab[in[i]];
+    }
+}
+
 extern "C" void nmsv_encode_ascii(const char* ascii, uint64_t n, uint8_t* codes)
 {
     for (uint64_t i = 0; i < n; ++i) {

@@ -31,6 +31,18 @@ def _scoring(s) -> Scoring:
     return Scoring(int(match), int(mismatch), int(gap_open), int(gap_extend))
 
 
+class AsciiSlice:
+    """A sequence that still lies, as ASCII, inside a larger buffer (a block of the seam TSV): it is encoded and packed in
+    one pass by nmsv_encode_pack when the SeqPack is finalized. `src` is a uint8 array over the block (kept alive here)."""
+    __slots__ = ("src", "start", "length")
+
+    def __init__(self, src: np.ndarray, start: int, length: int):
+        self.src, self.start, self.length = src, start, length
+
+    def __len__(self) -> int:
+        return self.length
+
+
 class SeqPack:
     """All sequences of one call in one uint8 code buffer: sequence i = codes[offsets[i] : offsets[i] + lens[i]]."""
 
@@ -51,6 +63,12 @@ class SeqPack:
         if self._dedup:
             self._seen[seq] = idx
         return idx
+
+    def add_ascii_slice(self, piece: AsciiSlice) -> int:
+        assert self._frozen is None, "SeqPack already finalized"
+        self._chunks.append(piece)
+        self._lens.append(piece.length)
+        return len(self._lens) - 1
 
     def add_codes(self, codes: np.ndarray) -> int:
         assert self._frozen is None, "SeqPack already finalized"
@@ -76,8 +94,19 @@ class SeqPack:
                 np.cumsum(padded[:-1], out=offsets[1:])
             total = int(offsets[-1] + padded[-1]) if len(lens) else 0
             codes = np.full(total, 4, dtype=np.uint8)
-            for off, chunk in zip(offsets, self._chunks):
-                codes[int(off):int(off) + len(chunk)] = chunk
+            lazy: Dict[int, list] = {}          # id(source block) -> [(source, start, length, destination offset)]
+            for off, chunk in zip(offsets.tolist(), self._chunks):
+                if isinstance(chunk, AsciiSlice):
+                    lazy.setdefault(id(chunk.src), []).append((chunk.src, chunk.start, chunk.length, off))
+                else:
+                    codes[off:off + len(chunk)] = chunk
+            for items in lazy.values():         # one library call per source block: encode + pack in a single pass
+                src = items[0][0]
+                so = np.array([i[1] for i in items], dtype=np.uint64)
+                ln = np.array([i[2] for i in items], dtype=np.uint32)
+                do = np.array([i[3] for i in items], dtype=np.uint64)
+                _lib.load().nmsv_encode_pack(src.ctypes.data, so.ctypes.data, ln.ctypes.data, do.ctypes.data, len(items),
+                                             codes.ctypes.data)
             self._frozen = (codes, offsets, lens)
             self._chunks = []
         return self._frozen

@@ -145,3 +145,61 @@ def test_synth_workload_is_deterministic_and_shaped():
     assert 12 * 10 <= n_t <= 12 * 30
     pack, svs, reads = a.to_batch("tumor")
     assert len(svs) == 12 and len(reads) == n_t
+
+
+class _RecordingEngine:
+    """Stands in for the GPU engine: keeps every batch it is handed (host logic only)."""
+
+    def __init__(self):
+        self.batches = []
+
+    def validate(self, pack, svs, reads, scoring=None):
+        codes, offsets, lens = pack.finalize()
+        self.batches.append((codes.copy(), offsets.copy(), lens.copy(), svs.copy(), reads.copy()))
+        checked = np.array([int(e) - int(b) for b, e in zip(svs["read_begin"], svs["read_end"])], dtype=np.int32)
+        return checked, np.zeros(len(svs), dtype=np.int32), np.zeros(0, dtype=_lib.RECORD_DTYPE)
+
+
+@pytest.mark.parametrize("sbnd", [False, True])
+def test_byte_level_seam_reader_builds_the_same_batches(tmp_path, monkeypatch, sbnd):
+    """The block / memchr / nmsv_encode_pack reader (default) against the line-by-line reader that mirrors the
+    reference's loop (:414-425): identical code buffers, SV and read tables, count files -- including CR LF line ends,
+    a last line without newline, repeated read ids (last record wins), empty sequences (mapq kept, read dropped),
+    'None' mapqs, soft-masked and N bases, and blocks that end in the middle of a line."""
+    cfg = synth.PRESETS["single_breakend" if sbnd else "testdata_shaped"]
+    import dataclasses
+    cfg = dataclasses.replace(cfg, n_sv=6, coverage=6.0, read_len_mean=900, read_len_min=300, read_len_max=2000,
+                              contig_len=80000, n_contigs=2, seed=5, **({} if sbnd else {"short_fraction": 0.5}))
+    wl = synth.make_workload(cfg, samples=("tumor",))
+    seam = str(tmp_path / "seam.tsv")
+    wl.write_seam("tumor", seam)
+    lines = open(seam).read().splitlines()
+    k0 = lines[0].split("\t")[0]
+    extra = [f"{k0}\tdup_read\t60\t60\tACGTNNacgt" + "ACGT" * 50, f"{k0}\tdup_read\tNone\t30\t" + "TTGCA" * 40,   # same id twice
+             f"{k0}\tempty_read\t60\t60\t", f"{k0}\tspaced id tail\t12\tNone\t  " + "GATTACA" * 30 + " "]
+    body = "\r\n".join(extra + lines)                        # CR LF everywhere, no newline after the last line
+    open(seam, "w", newline="").write(body)
+    out = {}
+    for reader, chunk in (("lines", None), ("bytes", None), ("bytes", 4096)):
+        monkeypatch.setenv("NMSV_SEAM_READER", reader)
+        monkeypatch.setattr(C, "SEAM_CHUNK_BYTES", chunk or (64 << 20))
+        eng = _RecordingEngine()
+        fc, fi = str(tmp_path / f"{reader}{chunk}.count"), str(tmp_path / f"{reader}{chunk}.info")
+        C.count_sread_from_seam(seam, fc, fi, wl.fasta, sbnd, 40, 1.2, engine=eng)
+        out[(reader, chunk)] = (eng.batches, open(fc).read())
+    ref_batches, ref_count = out[("lines", None)]
+    assert len(ref_batches) == 1 and ref_count.count("\n") == 6
+    for key in (("bytes", None), ("bytes", 4096)):
+        batches, count = out[key]
+        assert count == ref_count and len(batches) == len(ref_batches)
+        for a, b in zip(ref_batches, batches):
+            for x, y in zip(a, b):
+                assert x.dtype == y.dtype and x.shape == y.shape and (x == y).all(), key
+    # the extra lines did what they are there for
+    codes, offsets, lens, svs, reads = ref_batches[0]
+    n_first = int(svs["read_end"][0]) - int(svs["read_begin"][0])
+    assert n_first == sum(1 for ln in lines if ln.split("\t")[0] == k0) + 2   # dup_read once, empty_read dropped
+    with pytest.raises(ValueError):
+        open(seam, "a").write("\nbroken line without tabs\n")
+        monkeypatch.setenv("NMSV_SEAM_READER", "bytes")
+        C.count_sread_from_seam(seam, fc, fi, wl.fasta, sbnd, 40, 1.2, engine=_RecordingEngine())
