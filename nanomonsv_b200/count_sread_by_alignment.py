@@ -479,8 +479,9 @@ def count_sread_from_seam(seam_file, output_count_file, output_alignment_info_fi
     """The part of count_sread_by_alignment after read gathering: seam TSV -> sread_count / sread_info files."""
     counter = Alignment_counter(output_count_file, output_alignment_info_file, reference_fasta, var_read_min_mapq,
                                 score_ratio_thres, False, debug, engine=engine, **kwargs)
-    reader = kwargs_reader if (kwargs_reader := os.environ.get("NMSV_SEAM_READER")) else "bytes"
-    (_stream_seam if reader == "lines" else _stream_seam_fast)(seam_file, counter, is_sbnd)
+    # NMSV_SEAM_READER=lines selects the line-by-line reader that mirrors the reference's loop
+    reader = _stream_seam if os.environ.get("NMSV_SEAM_READER", "bytes") == "lines" else _stream_seam_fast
+    reader(seam_file, counter, is_sbnd)
     return counter
 
 
