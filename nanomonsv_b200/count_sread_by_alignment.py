@@ -399,62 +399,54 @@ class Alignment_counter(object):
             pass
 
 
-SEAM_CHUNK_BYTES = int(os.environ.get("NMSV_SEAM_CHUNK", str(64 << 20)))
 _WS = b" \t\r\n\x0b\x0c"
 
 
 def _stream_seam_fast(seam_file: str, counter: Alignment_counter, is_sbnd: bool) -> None:
-    """The same group-by as _stream_seam, on bytes: the file is read in large blocks, the five fields of a line are
-    located with bytes.find (memchr), and every read reaches the batch as a slice of the block it was read in; the
-    library encodes and packs all of them in one pass when the batch is finalized (nmsv_encode_pack) -- no per-read
-    str objects, no per-read encoding, no intermediate copies. The line-by-line reader stays as the executable
-    specification (tests/test_abi_and_host.py holds the two to identical batches)."""
+    """The same group-by as _stream_seam, on bytes: the file is memory-mapped, the five fields of a line are located with
+    find (memchr), and every read reaches the batch as a slice of the mapping; the library encodes and packs all of them
+    in one pass when the batch is finalized (nmsv_encode_pack) -- no per-read str objects, no per-read encoding, no
+    intermediate copies. The line-by-line reader stays as the executable specification
+    (tests/test_abi_and_host.py holds the two to identical batches)."""
+    import mmap
+
     def close_group():
         if counter.temp_key is not None:
             counter.count_alignment_and_print_sbnd() if is_sbnd else counter.count_alignment_and_print()
 
-    cur_key = None                         # bytes of the key column of the open group
     with open(seam_file, "rb") as hin:
-        rest = b""
-        while True:
-            block = hin.read(SEAM_CHUNK_BYTES)
-            data = rest + block
-            if block:
-                cut = data.rfind(b"\n") + 1
-                data, rest = data[:cut], data[cut:]        # whole lines now, the partial last line with the next block
-            else:
-                rest = b""
-                if data and not data.endswith(b"\n"):
-                    data += b"\n"
-            if data:
-                src = np.frombuffer(data, dtype=np.uint8)      # the reads stay ASCII in this block until the batch is packed
-                find = data.find
-                pos, n = 0, len(data)
-                while pos < n:
-                    le = find(b"\n", pos)
-                    t0 = find(b"\t", pos, le)
-                    t1 = find(b"\t", t0 + 1, le)
-                    t2 = find(b"\t", t1 + 1, le)
-                    t3 = find(b"\t", t2 + 1, le)
-                    if t0 < 0 or t1 < 0 or t2 < 0 or t3 < 0 or find(b"\t", t3 + 1, le) >= 0:
-                        raise ValueError(f"{seam_file}: a line does not have 5 tab-separated fields")
-                    kb = data[pos:t0]
-                    if kb != cur_key:
-                        close_group()
-                        counter.initialize(kb.decode(), is_sbnd=is_sbnd)
-                        cur_key = kb
-                    a, b = t3 + 1, le
-                    while b > a and data[b - 1] in _WS:          # str.strip() of the line-by-line reader (e.g. CR LF files)
-                        b -= 1
-                    while a < b and data[a] in _WS:
-                        a += 1
-                    counter._add_encoded_read(data[t0 + 1:t1], AsciiSlice(src, a, b - a), data[t1 + 1:t2],
-                                              None if is_sbnd else data[t2 + 1:t3])
-                    pos = le + 1
-            if not block:
-                break
+        size = os.fstat(hin.fileno()).st_size
+        if size:
+            data = mmap.mmap(hin.fileno(), 0, access=mmap.ACCESS_READ)
+            src = np.frombuffer(data, dtype=np.uint8)          # the reads stay ASCII in the mapping until a batch is packed
+            find = data.find
+            cur_key = None                                     # bytes of the key column of the open group
+            pos = 0
+            while pos < size:
+                le = find(b"\n", pos)
+                if le < 0:
+                    le = size                                  # last line without a newline
+                t0 = find(b"\t", pos, le)
+                t1 = find(b"\t", t0 + 1, le)
+                t2 = find(b"\t", t1 + 1, le)
+                t3 = find(b"\t", t2 + 1, le)
+                if t0 < 0 or t1 < 0 or t2 < 0 or t3 < 0 or find(b"\t", t3 + 1, le) >= 0:
+                    raise ValueError(f"{seam_file}: a line does not have 5 tab-separated fields")
+                kb = data[pos:t0]
+                if kb != cur_key:
+                    close_group()
+                    counter.initialize(kb.decode(), is_sbnd=is_sbnd)
+                    cur_key = kb
+                a, b = t3 + 1, le
+                while b > a and data[b - 1] in _WS:            # str.strip() of the line-by-line reader (e.g. CR LF files)
+                    b -= 1
+                while a < b and data[a] in _WS:
+                    a += 1
+                counter._add_encoded_read(data[t0 + 1:t1], AsciiSlice(src, a, b - a), data[t1 + 1:t2],
+                                          None if is_sbnd else data[t2 + 1:t3])
+                pos = le + 1
     close_group()
-    counter.close()
+    counter.close()          # waits for the batches in flight: their slices keep the mapping alive until then
 
 
 def _stream_seam(seam_file: str, counter: Alignment_counter, is_sbnd: bool) -> None:

@@ -165,7 +165,7 @@ def test_byte_level_seam_reader_builds_the_same_batches(tmp_path, monkeypatch, s
     """The block / memchr / nmsv_encode_pack reader (default) against the line-by-line reader that mirrors the
     reference's loop (:414-425): identical code buffers, SV and read tables, count files -- including CR LF line ends,
     a last line without newline, repeated read ids (last record wins), empty sequences (mapq kept, read dropped),
-    'None' mapqs, soft-masked and N bases, and blocks that end in the middle of a line."""
+    'None' mapqs, soft-masked and N bases, one batch and several batches."""
     cfg = synth.PRESETS["single_breakend" if sbnd else "testdata_shaped"]
     import dataclasses
     cfg = dataclasses.replace(cfg, n_sv=6, coverage=6.0, read_len_mean=900, read_len_min=300, read_len_max=2000,
@@ -180,23 +180,24 @@ def test_byte_level_seam_reader_builds_the_same_batches(tmp_path, monkeypatch, s
     body = "\r\n".join(extra + lines)                        # CR LF everywhere, no newline after the last line
     open(seam, "w", newline="").write(body)
     out = {}
-    for reader, chunk in (("lines", None), ("bytes", None), ("bytes", 4096)):
+    for reader, batch_bases in (("lines", 512 << 20), ("bytes", 512 << 20), ("lines", 20000), ("bytes", 20000)):
         monkeypatch.setenv("NMSV_SEAM_READER", reader)
-        monkeypatch.setattr(C, "SEAM_CHUNK_BYTES", chunk or (64 << 20))
+        monkeypatch.setattr(C, "BATCH_BASES", batch_bases)       # 20000: several batches in flight behind the parser
         eng = _RecordingEngine()
-        fc, fi = str(tmp_path / f"{reader}{chunk}.count"), str(tmp_path / f"{reader}{chunk}.info")
+        fc, fi = str(tmp_path / f"{reader}{batch_bases}.count"), str(tmp_path / f"{reader}{batch_bases}.info")
         C.count_sread_from_seam(seam, fc, fi, wl.fasta, sbnd, 40, 1.2, engine=eng)
-        out[(reader, chunk)] = (eng.batches, open(fc).read())
-    ref_batches, ref_count = out[("lines", None)]
-    assert len(ref_batches) == 1 and ref_count.count("\n") == 6
-    for key in (("bytes", None), ("bytes", 4096)):
+        out[(reader, batch_bases)] = (eng.batches, open(fc).read())
+    ref_batches, ref_count = out[("lines", 512 << 20)]
+    assert len(ref_batches) == 1 and ref_count.count("\n") == 6 and len(out[("lines", 20000)][0]) > 1
+    for key, ref_key in ((("bytes", 512 << 20), ("lines", 512 << 20)), (("bytes", 20000), ("lines", 20000))):
         batches, count = out[key]
+        ref_batches, ref_count = out[ref_key]
         assert count == ref_count and len(batches) == len(ref_batches)
         for a, b in zip(ref_batches, batches):
             for x, y in zip(a, b):
                 assert x.dtype == y.dtype and x.shape == y.shape and (x == y).all(), key
     # the extra lines did what they are there for
-    codes, offsets, lens, svs, reads = ref_batches[0]
+    codes, offsets, lens, svs, reads = out[("lines", 512 << 20)][0][0]
     n_first = int(svs["read_end"][0]) - int(svs["read_begin"][0])
     assert n_first == sum(1 for ln in lines if ln.split("\t")[0] == k0) + 2   # dup_read once, empty_read dropped
     with pytest.raises(ValueError):
