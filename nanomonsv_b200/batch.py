@@ -80,6 +80,18 @@ class BatchBuilder:
                             _lib.MAPQ_NONE if mapq2 is None else int(mapq2)))
         return len(self._reads) - 1
 
+    def read_seq_index(self, read_row: int) -> int:
+        return self._reads[read_row][0]
+
+    def add_read_shared(self, seq_index: int, mapq1: Optional[int], mapq2: Optional[int]) -> int:
+        """A read whose sequence is already in the pack (the same read serves several SV candidates, reference
+        count_sread_by_alignment.py:109-111): only a row of the read table is added."""
+        assert self._open_sv is not None, "add_sv first"
+        self.bases += self.pack.length(seq_index)
+        self._reads.append((seq_index, self._open_sv, _lib.MAPQ_NONE if mapq1 is None else int(mapq1),
+                            _lib.MAPQ_NONE if mapq2 is None else int(mapq2)))
+        return len(self._reads) - 1
+
     def _close_sv(self):
         if self._open_sv is not None:
             self._svs[self._open_sv][3] = len(self._reads)

@@ -57,12 +57,9 @@ def _get_alignment_object(alignment_file, reference_fasta):
     return pysam.AlignmentFile(alignment_file, "rb")
 
 
-def gather_local_read_for_realignment(sv_file, alignment_file, output_file, reference_fasta,
-                                      sbnd_file=None, output_file_sbnd=None, validate_sequence_length=200,
-                                      check_read_max_num=500, sort_option=None):
-    """Writes `key \\t qname \\t mapq1 \\t mapq2 \\t sequence` for every primary read near a breakpoint, sorted by
-    key with GNU sort (reference :27-134). check_read_max_num is accepted and, as in the reference, not forwarded."""
-    alignment_h = _get_alignment_object(alignment_file, reference_fasta)
+def _window_pass(alignment_h, sv_file, sbnd_file, validate_sequence_length):
+    """First pass of the gathering (reference :31-88): which reads lie in a +-100 bp window of which breakpoint, and
+    with which mapping quality (the last record of a read name in a window wins, whatever its flags)."""
     rname2key: Dict[str, list] = {}
     key2rname2mapq: Dict[str, dict] = {}
     with open(sv_file) as hin:
@@ -96,6 +93,18 @@ def gather_local_read_for_realignment(sv_file, alignment_file, output_file, refe
         for rname in rname2key_sbnd:
             rname2key_sbnd[rname] = list(set(rname2key_sbnd[rname]))
 
+    return rname2key, key2rname2mapq, rname2key_sbnd, key2rname2mapq_sbnd
+
+
+def gather_local_read_for_realignment(sv_file, alignment_file, output_file, reference_fasta,
+                                      sbnd_file=None, output_file_sbnd=None, validate_sequence_length=200,
+                                      check_read_max_num=500, sort_option=None):
+    """Writes `key \\t qname \\t mapq1 \\t mapq2 \\t sequence` for every primary read near a breakpoint, sorted by
+    key with GNU sort (reference :27-134). check_read_max_num is accepted and, as in the reference, not forwarded."""
+    alignment_h = _get_alignment_object(alignment_file, reference_fasta)
+    rname2key, key2rname2mapq, rname2key_sbnd, key2rname2mapq_sbnd = _window_pass(alignment_h, sv_file, sbnd_file,
+                                                                                  validate_sequence_length)
+
     hout = open(output_file + ".tmp.unsorted", "w")
     hout_sbnd = open(output_file_sbnd + ".tmp.unsorted", "w") if sbnd_file is not None else None
     for read in alignment_h.fetch():
@@ -128,6 +137,64 @@ def gather_local_read_for_realignment(sv_file, alignment_file, output_file, refe
     if sbnd_file is not None:
         gnu_sort(output_file_sbnd)
     alignment_h.close()
+
+
+def gather_reads_direct(sv_file, alignment_file, reference_fasta, sbnd_file=None, validate_sequence_length=200,
+                        sort_option=None):
+    """The gathering without the seam file: the same two passes over the alignment file as
+    gather_local_read_for_realignment, but the reads stay in memory -- no 'whole read per (read, key)' TSV, no GNU sort
+    of it, no re-parse -- and one str object per read is handed to every SV candidate the read serves, so that a batch
+    packs and uploads it once. Returns (groups, groups_sbnd): lists of (key, [(qname, mapq1, mapq2, sequence), ...]).
+
+    Order. The reference streams the key-sorted TSV, so its count file lists the keys in the collation order of GNU
+    `sort -k1,1` under the caller's locale: the (small) list of keys is therefore sorted by the same `sort` with the same
+    options. Within a key the TSV lines are ordered by the rest of the line; here by (read name, mapq1, mapq2, sequence)
+    as text in code-point order, which is that order under LC_ALL=C. Only two things see the within-key order: which
+    of two primary records with the SAME read name wins (the reference keeps the last, :162) and the order of a
+    candidate's supporting-read lines, which the reference itself leaves to set iteration (:325)."""
+    alignment_h = _get_alignment_object(alignment_file, reference_fasta)
+    rname2key, key2rname2mapq, rname2key_sbnd, key2rname2mapq_sbnd = _window_pass(alignment_h, sv_file, sbnd_file,
+                                                                                  validate_sequence_length)
+    per_key: Dict[str, list] = {}
+    per_key_sbnd: Dict[str, list] = {}
+    for read in alignment_h.fetch():
+        if read.is_supplementary or read.is_secondary or read.is_duplicate:
+            continue
+        in_main = read.qname in rname2key
+        in_sbnd = sbnd_file is not None and read.qname in rname2key_sbnd
+        if not (in_main or in_sbnd):
+            continue
+        read_seq = read.query_sequence
+        if read.is_reverse:
+            read_seq = reverse_complement(read_seq)
+        if in_main:
+            for key in rname2key[read.qname]:
+                mapq1, mapq2 = key2rname2mapq[key][read.qname]
+                per_key.setdefault(key, []).append((read.qname, mapq1, mapq2, read_seq))
+        if in_sbnd:
+            for key in rname2key_sbnd[read.qname]:
+                per_key_sbnd.setdefault(key, []).append((read.qname, key2rname2mapq_sbnd[key][read.qname], None, read_seq))
+    alignment_h.close()
+
+    def in_sort_order(groups: Dict[str, list]) -> list:
+        if not groups:
+            return []
+        proc = subprocess.run(["sort", "-k1,1"] + (sort_option.split(" ") if sort_option else []),
+                              input="".join(k + "\n" for k in groups), capture_output=True, text=True, check=True)
+        keys = proc.stdout.splitlines()
+        assert len(keys) == len(groups)
+        return [(k, sorted(groups[k], key=lambda r: (r[0], str(r[1]), str(r[2]), r[3]))) for k in keys]
+
+    return in_sort_order(per_key), in_sort_order(per_key_sbnd)
+
+
+def _count_from_groups(groups, counter: "Alignment_counter", is_sbnd: bool) -> None:
+    for key, rows in groups:
+        counter.initialize(key, is_sbnd=is_sbnd)
+        for qname, mapq1, mapq2, seq in rows:
+            counter.add_long_read_seq(qname, seq, str(mapq1), "None" if is_sbnd else str(mapq2))
+        counter.count_alignment_and_print_sbnd() if is_sbnd else counter.count_alignment_and_print()
+    counter.close()
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -340,11 +407,19 @@ class Alignment_counter(object):
         eng = self._engine or default_engine()
         bb = BatchBuilder(self.score_ratio_thres, self.start_pos_thres, self.end_pos_thres,
                           self.var_ref_margin_thres, self.var_read_min_mapq)
-        for job in self._queue:
+        shared: Dict[int, int] = {}      # id(sequence object) -> index in this batch's pack: the direct gather hands the
+        for job in self._queue:          # SAME str object to every SV candidate a read serves, so it is packed once
             bb.add_sv(job.templates, job.is_sbnd, job.short)
             for rid in job.read_ids:
                 m1, m2 = job.read_mapq.get(rid, (None, None))
-                bb.add_read(job.read_seqs[rid], m1, m2)
+                seq = job.read_seqs[rid]
+                at = shared.get(id(seq)) if isinstance(seq, str) else None
+                if at is None:
+                    r = bb.add_read(seq, m1, m2)
+                    if isinstance(seq, str):
+                        shared[id(seq)] = bb.read_seq_index(r)
+                else:
+                    bb.add_read_shared(at, m1, m2)
         pack, svs, reads = bb.finalize()
         # The GPU call runs on a worker thread (ctypes releases the GIL), so the caller goes on parsing and encoding the
         # next batch meanwhile; results are written strictly in submission order (at the next flush, or at close()).
@@ -481,7 +556,18 @@ def count_sread_by_alignment(sv_file, alignment_file, output_count_file, output_
                              sbnd_file=None, output_count_file_sbnd=None, output_alignment_info_file_sbnd=None,
                              check_read_max_num=500, var_read_min_mapq=0, score_ratio_thres=1.2, use_ssw_lib=False,
                              sort_option=None, debug=False, engine: Optional[Engine] = None):
-    """Same signature as the reference (:401-403) plus an optional engine handle."""
+    """Same signature as the reference (:401-403) plus an optional engine handle. NMSV_DIRECT_GATHER=1 keeps the gathered
+    reads in memory instead of going through the sorted seam file (gather_reads_direct)."""
+    if os.environ.get("NMSV_DIRECT_GATHER", "0") == "1":
+        groups, groups_sbnd = gather_reads_direct(sv_file, alignment_file, reference_fasta, sbnd_file=sbnd_file,
+                                                  sort_option=sort_option)
+        _count_from_groups(groups, Alignment_counter(output_count_file, output_alignment_info_file, reference_fasta,
+                                                     var_read_min_mapq, score_ratio_thres, False, debug, engine=engine), False)
+        if sbnd_file is not None:
+            _count_from_groups(groups_sbnd, Alignment_counter(output_count_file_sbnd, output_alignment_info_file_sbnd,
+                                                              reference_fasta, var_read_min_mapq, score_ratio_thres, False,
+                                                              debug, engine=engine), True)
+        return
     seam = output_count_file + ".tmp.local_read_for_realignment"
     seam_sbnd = (output_count_file_sbnd + ".tmp.local_read_for_realignment") if output_count_file_sbnd is not None else None
     gather_local_read_for_realignment(sv_file, alignment_file, seam, reference_fasta, sbnd_file=sbnd_file,

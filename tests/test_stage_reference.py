@@ -105,3 +105,67 @@ def test_stage_function_reproduces_the_reference_run(fix, tmp_path, monkeypatch,
     assert open(out["count_sbnd"]).read().splitlines() == exp["count_sbnd"]
     assert sorted(open(out["info_sbnd"]).read().splitlines()) == sorted(exp["info_sbnd"])
     assert open(out["count"] + ".tmp.local_read_for_realignment").read().splitlines() == exp["seam"]
+
+
+class _RecordingEngine:
+    def __init__(self):
+        self.batches = []
+
+    def validate(self, pack, svs, reads, scoring=None):
+        import numpy as np
+        from nanomonsv_b200 import _lib
+        codes, offsets, lens = pack.finalize()
+        self.batches.append((codes.copy(), offsets.copy(), lens.copy(), svs.copy(), reads.copy()))
+        checked = np.array([int(e) - int(b) for b, e in zip(svs["read_begin"], svs["read_end"])], dtype=np.int32)
+        return checked, np.zeros(len(svs), dtype=np.int32), np.zeros(0, dtype=_lib.RECORD_DTYPE)
+
+
+def _per_sv_reads(batches):
+    """[(templates as code bytes, {(mapq1, mapq2, read as code bytes)})] over all batches, in SV order."""
+    out = []
+    for codes, offsets, lens, svs, reads in batches:
+        def seq(i):
+            return bytes(codes[int(offsets[i]):int(offsets[i]) + int(lens[i])])
+        for sv in svs:
+            tm = tuple(seq(int(t)) if int(t) != 0xffffffff else None for t in sv["tmpl"])
+            rs = {(int(r["mapq1"]), int(r["mapq2"]), seq(int(r["seq"]))) for r in reads[int(sv["read_begin"]):int(sv["read_end"])]}
+            out.append((tm, rs))
+    return out
+
+
+def test_direct_gather_builds_the_same_work(fix, tmp_path, monkeypatch):
+    """NMSV_DIRECT_GATHER=1 (reads kept in memory, no seam file, no sort of whole reads) hands the GPU the same SV
+    candidates in the same order with the same reads, mapqs and templates as the seam-file path -- and packs a read that
+    serves several candidates once."""
+    sv_file, sbnd_file = _write_inputs(fix, tmp_path)
+    monkeypatch.setattr(C, "_get_alignment_object", lambda a, r: Records(fix["records"]))
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("NMSV_DIRECT_GATHER", mode)
+        eng = _RecordingEngine()
+        out = {k: str(tmp_path / (k + mode)) for k in ("count", "info", "count_sbnd", "info_sbnd")}
+        C.count_sread_by_alignment(sv_file, "tumor.bam", out["count"], out["info"], O.DictFasta(fix["contigs"]),
+                                   sbnd_file=sbnd_file, output_count_file_sbnd=out["count_sbnd"],
+                                   output_alignment_info_file_sbnd=out["info_sbnd"], engine=eng, **fix["params"])
+        res[mode] = (eng.batches, open(out["count"]).read(), open(out["count_sbnd"]).read())
+        assert not os.path.exists(out["count"] + ".tmp.local_read_for_realignment")
+    assert res["0"][1] == res["1"][1] and res["0"][2] == res["1"][2]              # same candidates, same order, same read counts
+    assert _per_sv_reads(res["0"][0]) == _per_sv_reads(res["1"][0])
+    n_seq = {m: sum(len(b[2]) for b in res[m][0]) for m in res}
+    assert n_seq["1"] <= n_seq["0"]
+
+
+@pytest.mark.gpu
+def test_direct_gather_reproduces_the_reference_run(fix, tmp_path, monkeypatch, engine):
+    exp = fix["expected"]
+    sv_file, sbnd_file = _write_inputs(fix, tmp_path)
+    monkeypatch.setattr(C, "_get_alignment_object", lambda a, r: Records(fix["records"]))
+    monkeypatch.setenv("NMSV_DIRECT_GATHER", "1")
+    out = {k: str(tmp_path / k) for k in ("count", "info", "count_sbnd", "info_sbnd")}
+    C.count_sread_by_alignment(sv_file, "tumor.bam", out["count"], out["info"], O.DictFasta(fix["contigs"]),
+                               sbnd_file=sbnd_file, output_count_file_sbnd=out["count_sbnd"],
+                               output_alignment_info_file_sbnd=out["info_sbnd"], engine=engine, **fix["params"])
+    assert open(out["count"]).read().splitlines() == exp["count"]
+    assert sorted(open(out["info"]).read().splitlines()) == sorted(exp["info"])
+    assert open(out["count_sbnd"]).read().splitlines() == exp["count_sbnd"]
+    assert sorted(open(out["info_sbnd"]).read().splitlines()) == sorted(exp["info_sbnd"])
