@@ -114,11 +114,9 @@ def records_of(wl, sample, rng, sbnd):
     return recs
 
 
-def main():
-    ref = load_reference()
-    rng = np.random.default_rng(2026)
-    common = dict(coverage=6.0, read_len_mean=1300, read_len_min=500, read_len_max=2600, contig_len=120000, n_contigs=2, seed=77)
-    wl = synth.make_workload(dataclasses.replace(synth.PRESETS["testdata_shaped"], n_sv=8, short_fraction=0.5, **common),
+def build_inputs(seed, rng):
+    common = dict(coverage=6.0, read_len_mean=1300, read_len_min=500, read_len_max=2600, contig_len=120000, n_contigs=2, seed=seed)
+    wl = synth.make_workload(dataclasses.replace(synth.PRESETS["testdata_shaped"], n_sv=9, short_fraction=0.5, **common),
                              samples=("tumor",))
     swl = synth.make_workload(dataclasses.replace(synth.PRESETS["single_breakend"], n_sv=5, sbnd_contig_range=(100, 600),
                                                   sbnd_tail_range=(1200, 2500), **common), samples=("tumor",))
@@ -131,29 +129,51 @@ def main():
     contigs[k0[0]] = c[:p - 150] + c[p - 150:p - 120].lower() + c[p - 120:p + 40] + "N" * 6 + c[p + 46:]
     recs = records_of(wl, "tumor", rng, False) + records_of(swl, "tumor", rng, True)
     order = rng.permutation(len(recs))
-    recs = [recs[i] for i in order]
-    REGISTRY["records"], REGISTRY["contigs"] = recs, contigs
-    sv_lines = ["Chr_1\tPos_1\tDir_1\tChr_2\tPos_2\tDir_2\tInserted_Seq\tSV_ID"] + ["\t".join(s.key.split(",")) for s in wl.svs]
-    sbnd_lines = ["\t".join(s.key.split(",")) for s in swl.svs]
+    return wl, swl, contigs, [recs[i] for i in order]
+
+
+def live_short(f):
+    ins = 0 if f[6] == "---" else len(f[6])
+    return f[0] == f[3] and (f[2], f[5]) in (("+", "-"), ("-", "+")) and int(f[4]) - int(f[1]) + len(str(ins)) < 300
+
+
+def main():
+    ref = load_reference()
     params = dict(var_read_min_mapq=40, score_ratio_thres=1.2, sort_option="-S 64M")
-    with tempfile.TemporaryDirectory() as tmp:
-        fsv, fsb = os.path.join(tmp, "refined_bp.txt"), os.path.join(tmp, "refined_bp.sbnd.txt")
-        open(fsv, "w").write("".join(l + "\n" for l in sv_lines))
-        open(fsb, "w").write("".join(l + "\n" for l in sbnd_lines))
-        out = {k: os.path.join(tmp, k) for k in ("count", "info", "count_sbnd", "info_sbnd")}
-        ref.count_sread_by_alignment(fsv, os.path.join(tmp, "tumor.bam"), out["count"], out["info"], os.path.join(tmp, "ref.fa"),
-                                     sbnd_file=fsb, output_count_file_sbnd=out["count_sbnd"],
-                                     output_alignment_info_file_sbnd=out["info_sbnd"], debug=True, **params)
-        import gc
-        gc.collect()                                     # Alignment_counter.__del__ closes (flushes) the output files
-        produced = {k: open(v).read().splitlines() for k, v in out.items()}
-        produced["seam"] = open(out["count"] + ".tmp.local_read_for_realignment").read().splitlines()
-        produced["seam_sbnd"] = open(out["count_sbnd"] + ".tmp.local_read_for_realignment").read().splitlines()
+    for seed in range(77, 400):
+        # a seed whose candidates hold an insertion, short del/dup candidates of both orientations and long ones ...
+        rng = np.random.default_rng(2026 + seed)
+        wl, swl, contigs, recs = build_inputs(seed, rng)
+        ks = [s_.key.split(",") for s_ in wl.svs]
+        if not (any(f[6] != "---" for f in ks) and {(f[2], f[5]) for f in ks if live_short(f)} == {("+", "-"), ("-", "+")}
+                and sum(not live_short(f) for f in ks) >= 3 and {s_.key.split(",")[2] for s_ in swl.svs} == {"+", "-"}):
+            continue
+        REGISTRY["records"], REGISTRY["contigs"] = recs, contigs
+        sv_lines = ["Chr_1\tPos_1\tDir_1\tChr_2\tPos_2\tDir_2\tInserted_Seq\tSV_ID"] + ["\t".join(s_.key.split(",")) for s_ in wl.svs]
+        sbnd_lines = ["\t".join(s_.key.split(",")) for s_ in swl.svs]
+        with tempfile.TemporaryDirectory() as tmp:
+            fsv, fsb = os.path.join(tmp, "refined_bp.txt"), os.path.join(tmp, "refined_bp.sbnd.txt")
+            open(fsv, "w").write("".join(l + "\n" for l in sv_lines))
+            open(fsb, "w").write("".join(l + "\n" for l in sbnd_lines))
+            out = {k: os.path.join(tmp, k) for k in ("count", "info", "count_sbnd", "info_sbnd")}
+            ref.count_sread_by_alignment(fsv, os.path.join(tmp, "tumor.bam"), out["count"], out["info"], os.path.join(tmp, "ref.fa"),
+                                         sbnd_file=fsb, output_count_file_sbnd=out["count_sbnd"],
+                                         output_alignment_info_file_sbnd=out["info_sbnd"], debug=True, **params)
+            import gc
+            gc.collect()                                 # Alignment_counter.__del__ closes (flushes) the output files
+            produced = {k: open(v).read().splitlines() for k, v in out.items()}
+            produced["seam"] = open(out["count"] + ".tmp.local_read_for_realignment").read().splitlines()
+            produced["seam_sbnd"] = open(out["count_sbnd"] + ".tmp.local_read_for_realignment").read().splitlines()
+        # ... and whose run has supporting reads for insertion, short and long candidates and on the single-breakend pass
+        info_keys = {tuple(l.split("\t")[:8]) for l in produced["info"]}
+        if (len(produced["info_sbnd"]) >= 3 and any(k[6] != "---" for k in info_keys)
+                and any(live_short(list(k)) for k in info_keys) and any(not live_short(list(k)) for k in info_keys)):
+            break
     json.dump({"source": "nanomonsv/count_sread_by_alignment.py:401 run from /root/reference with stand-in pysam / parasail "
-                         "(tests/golden/make_golden_stage.py)",
+                         "(tests/golden/make_golden_stage.py)", "seed": seed,
                "contigs": contigs, "records": recs, "sv_file": sv_lines, "sbnd_file": sbnd_lines, "params": params,
                "expected": produced}, open(os.path.join(HERE, "stage_reference.json"), "w"), indent=0)
-    print({k: len(v) for k, v in produced.items()})
+    print("seed", seed, {k: len(v) for k, v in produced.items()})
 
 
 if __name__ == "__main__":
