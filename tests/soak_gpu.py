@@ -78,7 +78,7 @@ def main():
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     eng = Engine(0)
-    scorings = [(2, -2, 3, 1)] * 4 + [(1, -2, 3, 1), (2, -3, 5, 2), (3, -1, 2, 2), (2, -2, 1, 3), (2, 0, 4, 1), (1, -1, 0, 1)]
+    scorings = [(2, -2, 3, 1)] * 4 + [(1, -2, 3, 1), (2, -3, 5, 2), (3, -1, 2, 2), (2, -2, 1, 3), (2, 0, 4, 1), (1, -1, 0, 1), (2, -2, 4, 0)]
     t_end = time.time() + args.seconds
     n_pairs = n_batches = 0
     cells_total = 0.0

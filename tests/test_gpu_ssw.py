@@ -188,7 +188,8 @@ def test_begin_window_covers_long_insertions(engine):
     assert sorted(int(c["strand"]) for c in chk) == [-1] * 5 + [1] * 5
 
 
-@pytest.mark.parametrize("scoring", [(1, -2, 3, 1), (2, -3, 5, 2), (3, -1, 2, 2), (2, -2, 3, 3), (2, 0, 4, 1)])
+@pytest.mark.parametrize("scoring", [(1, -2, 3, 1), (2, -3, 5, 2), (3, -1, 2, 2), (2, -2, 3, 3), (2, 0, 4, 1),
+                                     (2, -2, 4, 0), (1, -1, 0, 1), (2, -2, 0, 0)])
 def test_other_scorings(engine, scoring):
     """The other parasail.ssw call sites use other matrices (locate_bp_sbnd.py:28 uses 1/-2)."""
     rnd = random.Random(hash(scoring) & 0xffff)
