@@ -34,12 +34,13 @@
 extern "C" {
 #endif
 
-#define NMSV_ABI_VERSION 1
+#define NMSV_ABI_VERSION 2
 
 #define NMSV_OK 0
 #define NMSV_E_INVALID (-1)   /* bad argument (NULL pointer, empty sequence, index out of range ...) */
 #define NMSV_E_CUDA (-2)      /* a CUDA runtime call failed */
-#define NMSV_E_RANGE (-3)     /* a score could exceed the 16-bit lanes (parasail would return NULL) */
+#define NMSV_E_RANGE (-3)     /* scoring parameters too large for 16-bit lanes, or (stage seam) an alignment whose score
+                                 left the 16-bit range: parasail.ssw returns None and the reference's ssw_check fails */
 #define NMSV_E_CAPACITY (-4)  /* caller's record buffer too small; *n_records holds the required count */
 #define NMSV_E_INTERNAL (-5)  /* device-side consistency check failed */
 
@@ -66,7 +67,11 @@ typedef struct {
 } nmsv_scoring;
 
 /* Result fields of parasail.ssw as read at count_sread_by_alignment.py:151-159 (0-based, inclusive).
- * "read" = s1 (the template), "ref" = s2 (the long read).  score1 = -1: not representable in 16 bits. */
+ * "read" = s1 (the template), "ref" = s2 (the long read).  score1 = -1 (all fields -1): the score is not
+ * representable in 16 bits, parasail.ssw returns None (generate_consensus.py:120-125 handles that per pair).
+ * There is no limit on sequence lengths: like parasail the engine only gives up when a score actually reaches the
+ * 16-bit limit (it reports None for scores above sw_score_cap - 32*match = 32518 with the reference's scoring,
+ * parasail above 32764 -- the one documented divergence). */
 typedef struct {
     int32_t score1;
     int32_t ref_begin1;
@@ -125,15 +130,23 @@ typedef struct {
 /* Work/launch accounting of the last run of a plan (for GCUPS reporting). */
 typedef struct {
     uint64_t cells_reference;  /* forward DP cells the reference would compute: sum n*m over every alignment */
-    uint64_t cells_executed;   /* forward DP cells actually computed on the device (identical templates shared) */
-    uint64_t cells_padded;     /* cells issued including row padding of the last tile and pipeline skew */
-    uint64_t fwd_tasks;        /* (read, template pair) wavefront tasks */
-    uint64_t rev_tasks;        /* begin-coordinate (reversed window) tasks */
+    uint64_t cells_executed;   /* forward DP cells computed on the device in the last run (counted on the device) */
+    uint64_t cells_padded;     /* cells issued by the statically planned tasks incl. row padding and pipeline skew */
+    uint64_t fwd_tasks;        /* statically planned (read, template pair) wavefront tasks */
+    uint64_t rev_tasks;        /* begin-coordinate (reversed window) tasks of the last run */
     uint32_t kernel_launches;  /* kernels launched by one nmsv_plan_run */
     uint32_t n_classes;        /* row-strip classes (kernel instantiations) used */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
     uint64_t workspace_bytes;
+    /* ABI 2 */
+    uint64_t cells_dedup;      /* cells_reference minus the repeats of identical templates of one SV (var1 == var2) */
+    uint64_t cells_pruned;     /* cells_dedup - cells_executed: alignments that cannot change any output (reads whose
+                                  mapq test fails, :344-346; reference alleles of reads that fail the variant tests, :336-341) */
+    uint64_t cells_begin;      /* begin-pass cells of the last run (overhead, in no GCUPS figure) */
+    uint64_t fwd_tasks_queued; /* reference-allele forward tasks queued on the device in the last run */
+    uint32_t reads_pruned;     /* reads counted as checked without any alignment */
+    uint32_t reserved;
 } nmsv_stats;
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
@@ -141,6 +154,11 @@ int nmsv_abi_version(void);
 int nmsv_create(nmsv_ctx **ctx, int device);          /* one ctx per process/GPU (mirrors --processes, run.py:367) */
 void nmsv_destroy(nmsv_ctx *ctx);
 const char *nmsv_last_error(const nmsv_ctx *ctx);     /* ctx may be NULL: error of a failed nmsv_create */
+/* options: "prune" (default 1): skip alignments that cannot change any output of the stage seam -- reads whose mapq
+ * test already fails are only counted (count_sread_by_alignment.py:344-346, :388-389), ref1/ref2 are aligned only for
+ * reads that pass the variant tests (:336-341, :384-385). 0: every alignment the reference runs is computed (parity
+ * tests; nmsv_plan_download_alns then holds all of them). Counts and records are identical either way. */
+int nmsv_set_option(nmsv_ctx *ctx, const char *name, int value);
 int nmsv_set_stream(nmsv_ctx *ctx, void *cuda_stream); /* cudaStream_t to launch on; NULL = the ctx's own non-blocking
                                                           stream (pass cudaStreamLegacy to use the default stream) */
 int nmsv_device_info(const nmsv_ctx *ctx, int32_t *sm_count, int32_t *sm_clock_khz, int64_t *l2_bytes,

@@ -51,13 +51,17 @@ class Stats(ctypes.Structure):
     _fields_ = [("cells_reference", ctypes.c_uint64), ("cells_executed", ctypes.c_uint64),
                 ("cells_padded", ctypes.c_uint64), ("fwd_tasks", ctypes.c_uint64), ("rev_tasks", ctypes.c_uint64),
                 ("kernel_launches", ctypes.c_uint32), ("n_classes", ctypes.c_uint32), ("h2d_bytes", ctypes.c_uint64),
-                ("d2h_bytes", ctypes.c_uint64), ("workspace_bytes", ctypes.c_uint64)]
+                ("d2h_bytes", ctypes.c_uint64), ("workspace_bytes", ctypes.c_uint64),
+                ("cells_dedup", ctypes.c_uint64), ("cells_pruned", ctypes.c_uint64), ("cells_begin", ctypes.c_uint64),
+                ("fwd_tasks_queued", ctypes.c_uint64), ("reads_pruned", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
     def asdict(self) -> dict:
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
-EXPORTS = ["nmsv_abi_version", "nmsv_create", "nmsv_destroy", "nmsv_last_error", "nmsv_set_stream",
+ABI_VERSION = 2
+
+EXPORTS = ["nmsv_abi_version", "nmsv_create", "nmsv_destroy", "nmsv_last_error", "nmsv_set_stream", "nmsv_set_option",
            "nmsv_device_info", "nmsv_encode_ascii", "nmsv_encode_pack", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
            "nmsv_plan_create", "nmsv_plan_run", "nmsv_plan_download", "nmsv_plan_stats", "nmsv_plan_download_alns",
            "nmsv_plan_destroy", "nmsv_plan_set_profiling", "nmsv_plan_kernel_times", "nmsv_plan_copy_counts_device",
@@ -83,18 +87,29 @@ def load() -> ctypes.CDLL:
             if not os.path.exists(path):
                 raise RuntimeError(f"libnmsv_sw.so is not built and cannot be built here ({exc}); "
                                    "the validation engine has no CPU fallback") from exc
+            # the sources are newer than the library and the rebuild failed: running the old code silently would make
+            # every test of an edited kernel meaningless. Boxes without nvcc opt in explicitly.
+            if os.environ.get("NMSV_ALLOW_STALE", "0") != "1":
+                raise RuntimeError(f"libnmsv_sw.so is older than its sources and the rebuild failed ({exc}); "
+                                   "set NMSV_ALLOW_STALE=1 to load the stale library anyway") from exc
+            import warnings
+            warnings.warn(f"loading a STALE libnmsv_sw.so (rebuild failed: {exc})", RuntimeWarning)
     try:
         L = ctypes.CDLL(path)
     except OSError as exc:
         raise RuntimeError(f"cannot load {path}: {exc}; the validation engine has no CPU fallback") from exc
     vp, i32, u32, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64
     L.nmsv_abi_version.restype = ctypes.c_int
+    if L.nmsv_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{path} has ABI version {L.nmsv_abi_version()}, this package needs {ABI_VERSION}")
     L.nmsv_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
     L.nmsv_create.restype = ctypes.c_int
     L.nmsv_destroy.argtypes = [vp]
     L.nmsv_destroy.restype = None
     L.nmsv_last_error.argtypes = [vp]
     L.nmsv_last_error.restype = ctypes.c_char_p
+    L.nmsv_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    L.nmsv_set_option.restype = ctypes.c_int
     L.nmsv_set_stream.argtypes = [vp, vp]
     L.nmsv_set_stream.restype = ctypes.c_int
     L.nmsv_device_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(ctypes.c_int64),

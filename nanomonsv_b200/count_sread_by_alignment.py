@@ -467,11 +467,27 @@ class Alignment_counter(object):
             except Exception:
                 pass
 
+    # The reference writes every line inside count_alignment_and_print; here lines are written when a batch comes back
+    # from the GPU, so a caller that drives the class by hand must end with close() (or use it as a context manager).
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     def __del__(self):
+        unfinished = bool(getattr(self, "_queue", None)) or getattr(self, "_pending", None) is not None
         try:
             self.close()
-        except Exception:
-            pass
+        except Exception as exc:      # an error of the GPU batch must not vanish with the object
+            import warnings
+            warnings.warn(f"Alignment_counter for {getattr(self.hout_count, 'name', '?')} was dropped with unwritten "
+                          f"results and closing it failed: {exc!r}; the count / info files are incomplete", RuntimeWarning)
+        else:
+            if unfinished:
+                import warnings
+                warnings.warn("Alignment_counter was dropped without close(): its last batch was only written at "
+                              "garbage collection", RuntimeWarning)
 
 
 _WS = b" \t\r\n\x0b\x0c"

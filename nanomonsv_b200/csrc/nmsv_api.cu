@@ -73,6 +73,8 @@ struct nmsv_ctx {
     int sm_clock_khz = 0;
     int blocks_per_sm[8] = {0};
     void* snap = nullptr;      // per resident warp: column snapshots of the running-maximum tracker (nmsv_sw.cuh)
+    int prune = 1;             // nmsv_set_option("prune"): skip alignments that cannot change any output
+    int jump_bps = 0;          // resident blocks per SM of the sw_jump kernel (set once)
     mutable std::string error;
 };
 
@@ -178,6 +180,7 @@ extern "C" int nmsv_create(nmsv_ctx** out, int device)
     nmsv_ctx* ctx = new (std::nothrow) nmsv_ctx();
     if (!ctx) return set_err(nullptr, NMSV_E_INVALID, "nmsv_create: out of host memory");
     ctx->device = device;
+    { const char* e = getenv("NMSV_PRUNE"); if (e && e[0] == '0') ctx->prune = 0; }      // measurement knob
 #define CREATE_TRY(call)                                                                                       \
     do {                                                                                                       \
         cudaError_t e__ = (call);                                                                              \
@@ -222,6 +225,13 @@ extern "C" void nmsv_destroy(nmsv_ctx* ctx)
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
     if (ctx->snap) cudaFree(ctx->snap);
     delete ctx;
+}
+
+extern "C" int nmsv_set_option(nmsv_ctx* ctx, const char* name, int value)
+{
+    if (!ctx || !name) return NMSV_E_INVALID;
+    if (!strcmp(name, "prune")) { ctx->prune = value != 0; return NMSV_OK; }
+    return set_err(ctx, NMSV_E_INVALID, "nmsv_set_option: unknown option '%s'", name);
 }
 
 extern "C" int nmsv_set_stream(nmsv_ctx* ctx, void* cuda_stream)
@@ -361,8 +371,13 @@ struct Sel { int32_t score, erow, ecol, strand; };   // chosen strand of one (re
 
 // per strip class (index = position in the plan's class list, at most 8): forward queue head, begin queue head and
 // begin queue reservation count
-enum : uint32_t { kCntFwdQueue = 0, kCntRevQueue = 8, kCntRecords = 17, kCntStatus = 18, kCntRevReserve = 24, kCntTotal = 32 };
-enum : uint8_t { kReadCandidate = 1, kReadSupporting = 2 };
+enum : uint32_t { kCntFwdQueue = 0, kCntRevQueue = 8, kCntRecords = 17, kCntStatus = 18, kCntSaturated = 19,
+                  kCntRevReserve = 24, kCntTotal = 32 };
+// device work accounting (unsigned long long each)
+enum : uint32_t { kCellsFwd = 0, kCellsBegin = 1, kTasksSpawnedFwd = 2, kCellsTotal = 4 };
+enum : uint8_t { kReadCandidate = 1, kReadSupporting = 2,
+                 kReadPruned = 4,      // mapq test already failed: counted as checked, never aligned (:344-346, :388-389)
+                 kReadVarDone = 8 };   // lazy reference alleles: the variant alignments passed, ref1/ref2 are queued
 
 __device__ __forceinline__ int alias_of(const nmsv_sv& sv, int s)
 {
@@ -371,11 +386,55 @@ __device__ __forceinline__ int alias_of(const nmsv_sv& sv, int s)
     return s;
 }
 
+__device__ __forceinline__ bool slot_present(const nmsv_sv& sv, int s)
+{
+    if (sv.tmpl[s] == NMSV_NONE) return false;
+    if ((sv.flags & NMSV_SV_SBND) && (s == NMSV_SLOT_VAR2 || s == NMSV_SLOT_REF2)) return false;
+    return true;
+}
+
+// The mapping-quality test of the decision rules (count_sread_by_alignment.py:344-346, sbnd :388-389). It does not
+// depend on any alignment: a read that fails it is counted in `checked` and can never be supporting.
+__device__ __forceinline__ bool mapq_ok(const nmsv_sv& sv, const nmsv_read& rd)
+{
+    if (sv.flags & NMSV_SV_SBND) return rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq;
+    return rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq && rd.mapq2 != NMSV_MAPQ_NONE && rd.mapq2 >= sv.min_mapq;
+}
+
+// Reference-allele slots are only read by the margin tests (:336-341, :384-385), which only matter for a read that
+// already passed the variant tests: with lazy_refs their alignments are queued by the continuation of the variant tasks.
+__device__ __forceinline__ bool is_lazy_slot(const nmsv_sv& sv, int s)
+{
+    return (s == NMSV_SLOT_REF1 || s == NMSV_SLOT_REF2) && alias_of(sv, s) >= NMSV_SLOT_REF1;
+}
+
+__device__ __forceinline__ SwTask make_fwd_task(const nmsv_sv& sv, int s, uint32_t out, uint32_t read_seq,
+                                                const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ lens,
+                                                const uint8_t* __restrict__ seq_class)
+{
+    SwTask t;
+    memset(&t, 0, sizeof(t));
+    const uint32_t tm = sv.tmpl[s];
+    const uint32_t m = lens[tm];
+    t.out = out;
+    t.a_base = offsets[tm];
+    t.a_len = m;
+    const uint32_t rc = sv.tmpl_rc[s];
+    if (rc == NMSV_NONE) { t.b_base = offsets[tm] + m - 1; t.flags = kBRev | kBComp; }
+    else { t.b_base = offsets[rc]; }
+    t.b_len = m;
+    t.c_base = offsets[read_seq];
+    t.ncols = lens[read_seq];
+    t.rclass = (uint32_t)seq_class[tm];   // strip height R itself
+    return t;
+}
+
 // thread per (rank, slot): rank = position of the read in the cost-sorted order
 __global__ void plan_fwd_kernel(const nmsv_sv* __restrict__ svs, const nmsv_read* __restrict__ reads,
                                 const uint32_t* __restrict__ order, const uint64_t* __restrict__ offsets,
                                 const uint32_t* __restrict__ lens, const uint8_t* __restrict__ seq_class,
-                                uint32_t n_reads, SwTask* __restrict__ tasks, uint32_t* __restrict__ group_remaining)
+                                uint32_t n_reads, SwTask* __restrict__ tasks, uint32_t* __restrict__ group_remaining,
+                                uint8_t* __restrict__ read_flags, int prune, int lazy_refs)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_reads * 4u) return;
@@ -387,19 +446,10 @@ __global__ void plan_fwd_kernel(const nmsv_sv* __restrict__ svs, const nmsv_read
     memset(&t, 0, sizeof(t));
     t.out = r * 4u + (uint32_t)s;
     t.rclass = 0xffffffffu;
-    const uint32_t tm = sv.tmpl[s];
-    const bool sbnd_skip = (sv.flags & NMSV_SV_SBND) && (s == NMSV_SLOT_VAR2 || s == NMSV_SLOT_REF2);
-    if (tm != NMSV_NONE && !sbnd_skip && alias_of(sv, s) == s) {
-        const uint32_t m = lens[tm];
-        t.a_base = offsets[tm];
-        t.a_len = m;
-        const uint32_t rc = sv.tmpl_rc[s];
-        if (rc == NMSV_NONE) { t.b_base = offsets[tm] + m - 1; t.flags = kBRev | kBComp; }
-        else { t.b_base = offsets[rc]; }
-        t.b_len = m;
-        t.c_base = offsets[rd.seq];
-        t.ncols = lens[rd.seq];
-        t.rclass = (uint32_t)seq_class[tm];   // strip height R itself
+    const bool pruned = prune && !mapq_ok(sv, rd);
+    if (pruned && s == 0) read_flags[r] = kReadPruned;       // zeroed before the launch
+    if (!pruned && slot_present(sv, s) && alias_of(sv, s) == s && !(lazy_refs && is_lazy_slot(sv, s))) {
+        t = make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, offsets, lens, seq_class);
         if (t.ncols) atomicAdd(&group_remaining[r], 1u);      // zeroed before the launch
     }
     tasks[i] = t;
@@ -409,54 +459,38 @@ struct DecideParams {
     const nmsv_sv* svs; const nmsv_read* reads; const uint64_t* offsets; const uint32_t* lens;
     const uint8_t* seq_class; uint32_t n_reads;
     const SwResult* fwd; Sel* sel; uint8_t* read_flags;
-    // begin-pass queues: one region of rev_capacity entries per strip class in use (region_of_r: R -> region index)
+    // dynamic queues: one region of rev_capacity entries per strip class in use (region_of_r: R -> region index);
+    // begin-pass tasks and, with lazy_refs, the forward tasks of the reference alleles
     SwTask* rev_tasks; uint32_t* rev_ready; uint32_t rev_capacity; uint32_t* counters;
+    uint32_t* group_remaining; unsigned long long* cells;
     uint8_t region_of_r[kMaxR + 1];
     int match, open, ext;
+    int lazy_refs;
 };
 
 namespace nmsv { struct GroupHook { DecideParams d; }; }
 
-__device__ __forceinline__ bool slot_present(const nmsv_sv& sv, int s)
+// rows / columns an alignment of `score` that ends at (erow, ecol) can span at most: every gap position costs at least
+// min(open, ext), and an alignment over c columns (r rows) scores at most match * c (match * r)
+// (DESIGN.md "begin pass window")
+__device__ __forceinline__ uint32_t window_extent(int own, int other, int score, int match, int open, int ext)
 {
-    if (sv.tmpl[s] == NMSV_NONE) return false;
-    if ((sv.flags & NMSV_SV_SBND) && (s == NMSV_SLOT_VAR2 || s == NMSV_SLOT_REF2)) return false;
-    return true;
-}
-
-// columns an alignment of `score` that uses `rows` rows can span at most: every column-only gap position costs at
-// least min(open, ext) (DESIGN.md "begin pass window")
-__device__ __forceinline__ uint32_t window_cols(int rows, int score, int ecol, int match, int open, int ext)
-{
+    // own = extent available in this dimension (end coordinate + 1), other = extent available in the other one
     const int cmin = open < ext ? open : ext;
-    long long w = (long long)ecol + 1;
+    long long w = (long long)own;
     if (cmin > 0) {
-        long long slack = ((long long)match * rows - score) / cmin;
+        long long slack = ((long long)match * other - score) / cmin;
         if (slack < 0) slack = 0;
-        long long bound = (long long)rows + slack;
+        const long long bound = (long long)other + slack;
         if (bound < w) w = bound;
     }
     return (uint32_t)w;
 }
 
-__device__ __forceinline__ void emit_rev_task(const DecideParams& p, uint32_t out, uint32_t tm, uint32_t rc,
-                                              uint32_t read_seq, const Sel& sl)
+// publish a task in the dynamic queue of its strip class: body, fence, ready flag (a launch of that class may be
+// draining the queue right now)
+__device__ __forceinline__ void push_task(const DecideParams& p, const SwTask& t)
 {
-    const uint32_t m = p.lens[tm];
-    SwTask t;
-    memset(&t, 0, sizeof(t));
-    t.a_len = (uint32_t)sl.erow + 1u;
-    if (sl.strand > 0) { t.a_base = p.offsets[tm] + (uint64_t)sl.erow; t.flags = kARev; }               // reverse(T[0..e])
-    else if (rc == NMSV_NONE) { t.a_base = p.offsets[tm] + (uint64_t)(m - 1 - sl.erow); t.flags = kAComp; } // reverse(RC(T)[0..e])
-    else { t.a_base = p.offsets[rc] + (uint64_t)sl.erow; t.flags = kARev; }
-    t.b_len = 0;
-    t.c_base = p.offsets[read_seq] + (uint64_t)sl.ecol;
-    t.flags |= kCRev;
-    t.ncols = window_cols(sl.erow + 1, sl.score, sl.ecol, p.match, p.open, p.ext);
-    t.out = out;
-    t.best0 = (uint32_t)sl.score;       // only the cells that reach the forward score can be the begin cell
-    t.rclass = (uint32_t)p.seq_class[tm];
-    // publish: body, fence, ready flag (the forward launch of this class may be draining the queue right now)
     const uint32_t region = p.region_of_r[t.rclass];
     const uint32_t idx = atomicAdd(&p.counters[kCntRevReserve + region], 1u);
     const size_t at = (size_t)region * p.rev_capacity + idx;
@@ -465,30 +499,66 @@ __device__ __forceinline__ void emit_rev_task(const DecideParams& p, uint32_t ou
     atomicExch(&p.rev_ready[at], 1u);
 }
 
-// The decision for one read once all its forward alignments are known. Runs either as a thread of decide_kernel or,
-// on the fused path, on lane 0 of the warp that finished the read's last forward task (results of the other tasks come
-// from other SMs: L2 loads).
+__device__ __forceinline__ void emit_rev_task(const DecideParams& p, uint32_t out, uint32_t tm, uint32_t rc,
+                                              uint32_t read_seq, const Sel& sl)
+{
+    const uint32_t m = p.lens[tm];
+    SwTask t;
+    memset(&t, 0, sizeof(t));
+    // Every optimal alignment that ends in the end cell lies inside the window [erow - rows + 1, erow] x
+    // [ecol - cols + 1, ecol]; cells of the reversed prefixes inside a rectangle anchored at the end cell have the
+    // same values as in parasail's full second pass, cells outside cannot reach the score.
+    const uint32_t rows = window_extent(sl.erow + 1, sl.ecol + 1, sl.score, p.match, p.open, p.ext);
+    t.a_len = rows;
+    if (sl.strand > 0) { t.a_base = p.offsets[tm] + (uint64_t)sl.erow; t.flags = kARev; }               // reverse(T[0..e])
+    else if (rc == NMSV_NONE) { t.a_base = p.offsets[tm] + (uint64_t)(m - 1 - sl.erow); t.flags = kAComp; } // reverse(RC(T)[0..e])
+    else { t.a_base = p.offsets[rc] + (uint64_t)sl.erow; t.flags = kARev; }
+    t.b_len = 0;
+    t.c_base = p.offsets[read_seq] + (uint64_t)sl.ecol;
+    t.flags |= kCRev | kTaskBegin;
+    t.ncols = window_extent(sl.ecol + 1, sl.erow + 1, sl.score, p.match, p.open, p.ext);
+    t.out = out;
+    t.best0 = (uint32_t)sl.score;       // only the cells that reach the forward score can be the begin cell
+    t.rclass = (uint32_t)p.seq_class[tm];
+    push_task(p, t);
+}
+
+__device__ __forceinline__ Sel select_strand(const SwResult* fwd_slot)
+{
+    const int2* fp = reinterpret_cast<const int2*>(fwd_slot);
+    const int2 f0 = __ldcg(fp), f1 = __ldcg(fp + 1), f2 = __ldcg(fp + 2);      // results of other SMs: through L2
+    Sel x;
+    if (f0.x < 0 || f0.y < 0) { x.score = -1; x.erow = 0; x.ecol = 0; x.strand = 0; }   // saturated (parasail: None)
+    else if (f0.x > f0.y) { x.score = f0.x; x.erow = f1.x; x.ecol = f2.x; x.strand = 1; }
+    else { x.score = f0.y; x.erow = f1.y; x.ecol = f2.y; x.strand = -1; }                // ties -> '-'
+    return x;
+}
+
+// The decision for one read once the forward alignments it is waiting for are known. Runs either as a thread of
+// decide_kernel or, on the fused path, on lane 0 of the warp that finished the read's last outstanding forward task.
+// With lazy_refs it runs twice for a read whose SV has reference-allele slots: after the variant alignments (stage 1:
+// variant tests; a read that passes gets its ref1/ref2 alignments queued) and after those (stage 2).
 __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r)
 {
     const nmsv_read rd = p.reads[r];
     const nmsv_sv sv = p.svs[rd.sv];
+    const uint8_t state = p.read_flags[r];        // written only by this read's own chain of continuations
+    const bool stage1 = p.lazy_refs && !(state & kReadVarDone);
     Sel sl[4];
     bool present[4];
+    bool saturated = false;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         present[s] = slot_present(sv, s);
         Sel x = {0, 0, 0, 0};
-        if (present[s]) {
-            const int2* fp = reinterpret_cast<const int2*>(p.fwd + r * 4u + (uint32_t)alias_of(sv, s));
-            const int2 f0 = __ldcg(fp), f1 = __ldcg(fp + 1), f2 = __ldcg(fp + 2);
-            SwResult f;
-            f.score[0] = f0.x; f.score[1] = f0.y; f.row[0] = f1.x; f.row[1] = f1.y; f.col[0] = f2.x; f.col[1] = f2.y;
-            if (f.score[0] > f.score[1]) { x.score = f.score[0]; x.erow = f.row[0]; x.ecol = f.col[0]; x.strand = 1; }
-            else { x.score = f.score[1]; x.erow = f.row[1]; x.ecol = f.col[1]; x.strand = -1; }   // ties -> '-'
+        if (present[s] && !(stage1 && is_lazy_slot(sv, s))) {
+            x = select_strand(p.fwd + r * 4u + (uint32_t)alias_of(sv, s));
+            saturated |= x.score < 0;
         }
         sl[s] = x;
         p.sel[r * 4u + s] = x;
     }
+    if (saturated) { atomicAdd(&p.counters[kCntSaturated], 1u); p.read_flags[r] = 0; return; }
     const bool sbnd = sv.flags & NMSV_SV_SBND;
     bool pass = false;
     const int nvar = sbnd ? 1 : 2;
@@ -498,18 +568,36 @@ __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r
         if (sl[v].strand > 0) pass |= (sl[v].erow + 1 >= sv.qend_min[v]);        // qend   = read_end1 + 1
         else pass |= (m - sl[v].erow <= sv.qstart_max[v]);                       // qstart = m - read_end1_r
     }
+    pass = pass && mapq_ok(sv, rd);
+    if (stage1) {
+        if (!pass) { p.read_flags[r] = 0; return; }
+        uint32_t n = 0;
+        for (int s = NMSV_SLOT_REF1; s <= NMSV_SLOT_REF2; ++s)
+            n += (present[s] && alias_of(sv, s) == s && p.lens[rd.seq]) ? 1u : 0u;
+        if (n) {
+            p.read_flags[r] = kReadVarDone;
+            p.group_remaining[r] = n;          // published with the tasks (fence inside push_task)
+            atomicAdd(&p.cells[kTasksSpawnedFwd], (unsigned long long)n);
+            for (int s = NMSV_SLOT_REF1; s <= NMSV_SLOT_REF2; ++s)
+                if (present[s] && alias_of(sv, s) == s)
+                    push_task(p, make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, p.offsets, p.lens, p.seq_class));
+            return;
+        }
+        // no reference-allele alignment outstanding (no such slot, or they alias variant templates): decide now
+#pragma unroll
+        for (int s = NMSV_SLOT_REF1; s <= NMSV_SLOT_REF2; ++s)
+            if (present[s]) {
+                sl[s] = select_strand(p.fwd + r * 4u + (uint32_t)alias_of(sv, s));
+                p.sel[r * 4u + s] = sl[s];
+            }
+    }
     if (sbnd) {
         pass = pass && present[NMSV_SLOT_REF1] && sl[0].score >= sl[NMSV_SLOT_REF1].score + sv.margin;
-        pass = pass && rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq;
-    } else {
-        if (sv.flags & NMSV_SV_SHORT_DEL_DUP) {
-            const int r1 = sl[NMSV_SLOT_REF1].score + sv.margin, r2 = sl[NMSV_SLOT_REF2].score + sv.margin;
-            const bool ok1 = present[0] && sl[0].score >= r1 && sl[0].score >= r2;
-            const bool ok2 = present[1] && sl[1].score >= r1 && sl[1].score >= r2;
-            pass = pass && present[NMSV_SLOT_REF1] && present[NMSV_SLOT_REF2] && (ok1 || ok2);
-        }
-        pass = pass && rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq
-                    && rd.mapq2 != NMSV_MAPQ_NONE && rd.mapq2 >= sv.min_mapq;
+    } else if (sv.flags & NMSV_SV_SHORT_DEL_DUP) {
+        const int r1 = sl[NMSV_SLOT_REF1].score + sv.margin, r2 = sl[NMSV_SLOT_REF2].score + sv.margin;
+        const bool ok1 = present[0] && sl[0].score >= r1 && sl[0].score >= r2;
+        const bool ok2 = present[1] && sl[1].score >= r1 && sl[1].score >= r2;
+        pass = pass && present[NMSV_SLOT_REF1] && present[NMSV_SLOT_REF2] && (ok1 || ok2);
     }
     p.read_flags[r] = pass ? kReadCandidate : 0;
     if (!pass) return;
@@ -522,7 +610,7 @@ __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r
 __global__ void decide_kernel(const DecideParams p)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < p.n_reads) decide_read(p, r);
+    if (r < p.n_reads && !(p.read_flags[r] & kReadPruned)) decide_read(p, r);
 }
 
 __device__ void nmsv::sw_group_done(const GroupHook* hook, uint32_t out) { decide_read(hook->d, out >> 2); }
@@ -556,8 +644,8 @@ __global__ void final_kernel(const FinalParams p)
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         nmsv_aln a = {0, 0, 0, 0, 0, 0};
-        if (slot_present(sv, s)) {
-            const Sel sl = p.sel[r * 4u + s];
+        const Sel sl = p.sel[r * 4u + s];
+        if (slot_present(sv, s) && sl.strand != 0) {       // strand 0: never aligned (pruned read / lazy reference allele)
             const int m = (int)p.lens[sv.tmpl[s]];
             int brow = 0, bcol = 0;
             if (cand && sl.score > 0) {
@@ -636,7 +724,8 @@ __global__ void pair_decide_kernel(const PairParams p)
     if (i >= p.n_pairs) return;
     const SwResult f = p.fwd[i];
     Sel x;
-    if (!p.both_strands || f.score[0] > f.score[1]) { x.score = f.score[0]; x.erow = f.row[0]; x.ecol = f.col[0]; x.strand = 1; }
+    if (f.score[0] < 0 || (p.both_strands && f.score[1] < 0)) { x.score = -1; x.erow = 0; x.ecol = 0; x.strand = 0; }   // saturated
+    else if (!p.both_strands || f.score[0] > f.score[1]) { x.score = f.score[0]; x.erow = f.row[0]; x.ecol = f.col[0]; x.strand = 1; }
     else { x.score = f.score[1]; x.erow = f.row[1]; x.ecol = f.col[1]; x.strand = -1; }
     p.sel[i] = x;
     if (!p.want_begin || x.score <= 0) return;
@@ -653,6 +742,11 @@ __global__ void pair_final_kernel(const PairParams p)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_pairs) return;
     const Sel x = p.sel[i];
+    if (x.score < 0) {      // parasail.ssw returns None: the score is not representable in the 16-bit lanes
+        if (p.out_ssw) p.out_ssw[i] = nmsv_ssw_result{-1, -1, -1, -1, -1};
+        if (p.out_aln) p.out_aln[i] = nmsv_aln{-1, 0, 0, 0, 0, 0};
+        return;
+    }
     int brow = 0, bcol = 0;
     if (p.want_begin && x.score > 0) {
         const SwResult rv = p.rev[i];
@@ -704,12 +798,9 @@ static int check_template(nmsv_ctx* ctx, uint32_t idx, const uint32_t* lens, uin
 {
     if (idx >= n_seqs) return set_err(ctx, NMSV_E_INVALID, "%s index %u out of range (n_seqs %u)", what, idx, n_seqs);
     if (lens[idx] == 0) return set_err(ctx, NMSV_E_INVALID, "%s %u is empty", what, idx);
-    // parasail: NULL when any H exceeds INT16_MAX - max(matrix) - 1 ; H <= match * rows
-    // plus the kernel's bias head-room (nmsv_sw.cuh: sw_headroom)
-    if ((uint64_t)sc->match * lens[idx] + (uint64_t)sw_headroom(sc->gap_open, sc->gap_extend) >
-            32767u - (uint32_t)sc->match - 1u)
-        return set_err(ctx, NMSV_E_RANGE, "%s %u of length %u could score beyond the 16-bit range (parasail.ssw would return None)",
-                       what, idx, lens[idx]);
+    // No limit on the length: parasail returns NULL only when a score actually leaves the 16-bit range, and so does the
+    // kernel (a task whose bound match * min(rows, columns) exceeds sw_score_cap is watched at run time, nmsv_sw.cuh).
+    (void)sc;
     return NMSV_OK;
 }
 
@@ -760,8 +851,11 @@ struct nmsv_plan {
     nmsv_scoring sc{};
     SeqTables st;
     DevBuf svs, reads, order, tasks, fwd, rev_tasks, rev_ready, group_remaining, hook, rev, sel, alns, flags, supporting,
-           records, counters, bnd;
+           records, counters, cells, bnd;
     bool fused_begin = true;      // begin tasks are drained by the forward launches (NMSV_FUSED_BEGIN=0: separate launches only)
+    bool prune = true;            // reads whose mapq test fails get no alignments (nmsv_set_option "prune")
+    bool lazy_refs = true;        // ref1/ref2 alignments only for reads that pass the variant tests (needs the fused path)
+    uint32_t rev_capacity = 0;    // entries per strip class of the dynamic queue
     uint32_t bnd_stride = 1;
     std::vector<int> classes;          // indices into kClassR that occur in this batch
     std::vector<int32_t> checked;
@@ -841,7 +935,9 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
             pl->st.cls_host[sv.tmpl[s]] = (uint8_t)kClassR[c];
             class_used[c] = true;
         }
-        if ((sv.flags & NMSV_SV_SBND) && (sv.tmpl[NMSV_SLOT_VAR1] == NMSV_NONE || sv.tmpl[NMSV_SLOT_REF1] == NMSV_NONE))
+        if (sv.tmpl[NMSV_SLOT_VAR1] == NMSV_NONE)
+            return set_err(ctx, NMSV_E_INVALID, "SV %u has no variant template (var1)", i);
+        if ((sv.flags & NMSV_SV_SBND) && sv.tmpl[NMSV_SLOT_REF1] == NMSV_NONE)
             return set_err(ctx, NMSV_E_INVALID, "single-breakend SV %u needs var1 and ref1", i);
         if ((sv.flags & NMSV_SV_SHORT_DEL_DUP) && !(sv.flags & NMSV_SV_SBND) &&
             (sv.tmpl[NMSV_SLOT_REF1] == NMSV_NONE || sv.tmpl[NMSV_SLOT_REF2] == NMSV_NONE))
@@ -849,7 +945,14 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
     }
     for (int c = 0; c < kNumClasses; ++c) if (class_used[c]) pl->classes.push_back(c);
 
-    // ---- validate reads, cost-sort (longest first), work accounting
+    {
+        const char* e = getenv("NMSV_FUSED_BEGIN");
+        pl->fused_begin = !(e && e[0] == '0');
+    }
+    pl->prune = ctx->prune != 0;
+    pl->lazy_refs = pl->prune && pl->fused_begin;
+
+    // ---- validate reads, cost-sort, work accounting
     std::vector<uint64_t> cost(n_reads);
     uint32_t max_cols_multi = 0;
     nmsv_stats& stt = pl->stats;
@@ -860,24 +963,35 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
         const nmsv_sv& sv = svs[rd.sv];
         if (r < sv.read_begin || r >= sv.read_end) return set_err(ctx, NMSV_E_INVALID, "read %u is outside the read range of its SV %u", r, rd.sv);
         const uint64_t n = lens[rd.seq];
+        const bool sbnd = sv.flags & NMSV_SV_SBND;
+        const bool mq = sbnd ? (rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq)
+                             : (rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq && rd.mapq2 != NMSV_MAPQ_NONE && rd.mapq2 >= sv.min_mapq);
+        const bool pruned = pl->prune && !mq;
+        if (pruned) stt.reads_pruned += 1;
         uint64_t c = 0;
+        bool spawner = false;
         for (int s = 0; s < 4; ++s) {
             if (sv.tmpl[s] == NMSV_NONE) continue;
-            if ((sv.flags & NMSV_SV_SBND) && (s == NMSV_SLOT_VAR2 || s == NMSV_SLOT_REF2)) continue;
+            if (sbnd && (s == NMSV_SLOT_VAR2 || s == NMSV_SLOT_REF2)) continue;
             const uint64_t m = lens[sv.tmpl[s]];
             stt.cells_reference += 2 * m * n;
-            bool alias = false;
-            for (int q = 0; q < s; ++q) alias |= (sv.tmpl[q] == sv.tmpl[s] && sv.tmpl_rc[q] == sv.tmpl_rc[s]);
-            if (alias) continue;
+            int alias = s;
+            for (int q = s - 1; q >= 0; --q) if (sv.tmpl[q] == sv.tmpl[s] && sv.tmpl_rc[q] == sv.tmpl_rc[s]) alias = q;
+            if (alias != s) continue;
             const int cls = choose_class((uint32_t)m);
             const uint32_t nt = tiles_of((uint32_t)m, cls);
-            stt.cells_executed += 2 * m * n;
+            stt.cells_dedup += 2 * m * n;
+            if (nt > 1) max_cols_multi = std::max<uint32_t>(max_cols_multi, (uint32_t)n);
+            if (pruned) continue;
+            if (pl->lazy_refs && s >= NMSV_SLOT_REF1) { spawner = true; continue; }      // queued on the device, if at all
             stt.cells_padded += 2ull * nt * 32 * kClassR[cls] * (n + 31);
             stt.fwd_tasks += 1;
-            if (nt > 1) max_cols_multi = std::max<uint32_t>(max_cols_multi, (uint32_t)n);
             c += m * n;
         }
-        cost[r] = c;
+        // reads whose continuation can queue further forward work go first (their chain is three tasks deep), then
+        // longest first: the tail of the launch is then made of short, independent tasks
+        static const bool spawn_first = [] { const char* e = getenv("NMSV_SPAWN_FIRST"); return !(e && e[0] == '0'); }();   // measurement knob
+        cost[r] = c | (spawner && c && spawn_first ? (1ull << 62) : 0ull);
     }
     std::vector<uint32_t> order(n_reads);
     for (uint32_t r = 0; r < n_reads; ++r) order[r] = r;
@@ -903,14 +1017,14 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
     CUDA_TRY(ctx, pl->fwd.alloc(sizeof(SwResult) * nslots, s));
     const uint64_t n_regions = std::max<size_t>(1, pl->classes.size());
     if (n_regions > 8) return set_err(ctx, NMSV_E_INTERNAL, "more than 8 strip classes in one plan");
-    CUDA_TRY(ctx, pl->rev_tasks.alloc(sizeof(SwTask) * nslots * n_regions, s));
-    CUDA_TRY(ctx, pl->rev_ready.alloc(sizeof(uint32_t) * nslots * n_regions, s));
+    // per read at most 4 begin tasks and 2 queued reference-allele tasks
+    if ((uint64_t)n_reads * 6 > 0x7fffffffull) return set_err(ctx, NMSV_E_INVALID, "too many reads in one batch (%u)", n_reads);
+    pl->rev_capacity = n_reads * 6u;
+    CUDA_TRY(ctx, pl->rev_tasks.alloc(sizeof(SwTask) * (uint64_t)pl->rev_capacity * n_regions, s));
+    CUDA_TRY(ctx, pl->rev_ready.alloc(sizeof(uint32_t) * (uint64_t)pl->rev_capacity * n_regions, s));
     CUDA_TRY(ctx, pl->group_remaining.alloc(sizeof(uint32_t) * (uint64_t)n_reads, s));
     CUDA_TRY(ctx, pl->hook.alloc(sizeof(GroupHook), s));
-    {
-        const char* e = getenv("NMSV_FUSED_BEGIN");
-        pl->fused_begin = !(e && e[0] == '0');
-    }
+    CUDA_TRY(ctx, pl->cells.alloc(sizeof(unsigned long long) * kCellsTotal, s));
     CUDA_TRY(ctx, pl->rev.alloc(sizeof(SwResult) * nslots, s));
     CUDA_TRY(ctx, pl->sel.alloc(sizeof(Sel) * nslots, s));
     CUDA_TRY(ctx, pl->alns.alloc(sizeof(nmsv_aln) * nslots, s));
@@ -925,7 +1039,7 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
                           pl->group_remaining.bytes + pl->rev.bytes + pl->sel.bytes +
                           pl->alns.bytes + pl->flags.bytes + pl->supporting.bytes + pl->records.bytes + pl->bnd.bytes;
     stt.n_classes = (uint32_t)pl->classes.size();
-    stt.kernel_launches = (pl->fused_begin ? 2u : 3u) + 2 * stt.n_classes;
+    stt.kernel_launches = (pl->fused_begin ? 2u + 3 * stt.n_classes : 3u + 2 * stt.n_classes);
     // the caller's host buffers may be reused as soon as we return
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     guard.p = nullptr;
@@ -941,6 +1055,7 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     cudaStream_t s = ctx->stream;
     const uint32_t n_reads = pl->n_reads;
     CUDA_TRY(ctx, cudaMemsetAsync(pl->counters.p, 0, sizeof(uint32_t) * kCntTotal, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(pl->cells.p, 0, pl->cells.bytes, s));
     CUDA_TRY(ctx, cudaMemsetAsync(pl->supporting.p, 0, pl->supporting.bytes, s));
     pl->ran = true;
     if (n_reads == 0) return NMSV_OK;
@@ -953,9 +1068,13 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
 
     CUDA_TRY(ctx, cudaMemsetAsync(pl->group_remaining.p, 0, pl->group_remaining.bytes, s));
     CUDA_TRY(ctx, cudaMemsetAsync(pl->rev_ready.p, 0, pl->rev_ready.bytes, s));
+    // reads that never reach a decision (pruned, or no task at all) must read as "no alignment, not a candidate"
+    CUDA_TRY(ctx, cudaMemsetAsync(pl->flags.p, 0, pl->flags.bytes, s));
+    CUDA_TRY(ctx, cudaMemsetAsync(pl->sel.p, 0, pl->sel.bytes, s));
     plan_fwd_kernel<<<(nslots + tpb - 1) / tpb, tpb, 0, s>>>(pl->svs.as<nmsv_sv>(), pl->reads.as<nmsv_read>(),
         pl->order.as<uint32_t>(), pl->st.offsets.as<uint64_t>(), pl->st.lens.as<uint32_t>(), pl->st.seq_class.as<uint8_t>(),
-        n_reads, pl->tasks.as<SwTask>(), pl->group_remaining.as<uint32_t>());
+        n_reads, pl->tasks.as<SwTask>(), pl->group_remaining.as<uint32_t>(), pl->flags.as<uint8_t>(),
+        pl->prune ? 1 : 0, pl->lazy_refs ? 1 : 0);
     note(kPhasePlan, 0); mark(pl, ev, s);
 
     GroupHook hk;
@@ -964,8 +1083,10 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     dp.svs = pl->svs.as<nmsv_sv>(); dp.reads = pl->reads.as<nmsv_read>(); dp.offsets = pl->st.offsets.as<uint64_t>();
     dp.lens = pl->st.lens.as<uint32_t>(); dp.seq_class = pl->st.seq_class.as<uint8_t>(); dp.n_reads = n_reads;
     dp.fwd = pl->fwd.as<SwResult>(); dp.sel = pl->sel.as<Sel>(); dp.read_flags = pl->flags.as<uint8_t>();
-    dp.rev_tasks = pl->rev_tasks.as<SwTask>(); dp.rev_ready = pl->rev_ready.as<uint32_t>(); dp.rev_capacity = nslots;
+    dp.rev_tasks = pl->rev_tasks.as<SwTask>(); dp.rev_ready = pl->rev_ready.as<uint32_t>(); dp.rev_capacity = pl->rev_capacity;
     dp.counters = pl->counters.as<uint32_t>();
+    dp.group_remaining = pl->group_remaining.as<uint32_t>(); dp.cells = pl->cells.as<unsigned long long>();
+    dp.lazy_refs = pl->lazy_refs ? 1 : 0;
     for (size_t i = 0; i < pl->classes.size(); ++i) dp.region_of_r[kClassR[pl->classes[i]]] = (uint8_t)i;
     dp.match = pl->sc.match; dp.open = pl->sc.gap_open; dp.ext = pl->sc.gap_extend;
     if (pl->fused_begin) {      // the hook lives in device memory; the host copy is pageable, so this copy is staged before returning
@@ -978,39 +1099,54 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     sp.bnd = pl->bnd.as<uint2>(); sp.bnd_stride = pl->bnd_stride; sp.snap = (uint4*)ctx->snap;
     sp.match = pl->sc.match; sp.mismatch = pl->sc.mismatch; sp.open = pl->sc.gap_open; sp.ext = pl->sc.gap_extend;
     fill_packed(sp);
+    sp.fwd_results = pl->fwd.as<SwResult>(); sp.rev_results = pl->rev.as<SwResult>();
+    sp.cells = pl->cells.as<unsigned long long>();
 
-    // forward launches, one per strip class. Fused path: the warp that completes the last forward task of a read decides
-    // it and queues its begin tasks; the launch of the tasks' class drains that queue alongside its forward tasks.
-    sp.tasks = pl->tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = nslots; sp.results = pl->fwd.as<SwResult>();
+    // Forward launches, one per strip class. Fused path: the warp that completes the last outstanding forward task of a
+    // read runs its continuation (decide_read), which queues the read's reference-allele alignments or its begin tasks;
+    // the launch of the tasks' class drains that queue alongside its static list.
+    auto set_dyn = [&](size_t i) {
+        sp.hook = pl->hook.as<GroupHook>(); sp.group_remaining = pl->group_remaining.as<uint32_t>();
+        sp.dyn_tasks = dp.rev_tasks + i * (size_t)pl->rev_capacity; sp.dyn_ready = dp.rev_ready + i * (size_t)pl->rev_capacity;
+        sp.dyn_head = pl->counters.as<uint32_t>() + kCntRevQueue + i;
+        sp.dyn_reserve = pl->counters.as<uint32_t>() + kCntRevReserve + i;
+    };
+    sp.tasks = pl->tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = nslots;
     for (size_t i = 0; i < pl->classes.size(); ++i) {
         sp.queue_head = pl->counters.as<uint32_t>() + kCntFwdQueue + i;
-        if (pl->fused_begin) {
-            sp.hook = pl->hook.as<GroupHook>(); sp.group_remaining = pl->group_remaining.as<uint32_t>();
-            sp.dyn_tasks = dp.rev_tasks + i * (size_t)nslots; sp.dyn_ready = dp.rev_ready + i * (size_t)nslots;
-            sp.dyn_head = pl->counters.as<uint32_t>() + kCntRevQueue + i;
-            sp.dyn_reserve = pl->counters.as<uint32_t>() + kCntRevReserve + i;
-            sp.dyn_results = pl->rev.as<SwResult>();
-        }
+        if (pl->fused_begin) set_dyn(i);
         launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
         note(kPhaseFwd, (uint32_t)kClassR[pl->classes[i]]); mark(pl, ev, s);
     }
-    sp.hook = nullptr; sp.group_remaining = nullptr;
-    sp.dyn_tasks = nullptr; sp.dyn_ready = nullptr; sp.dyn_head = nullptr; sp.dyn_reserve = nullptr; sp.dyn_results = nullptr;
 
-    if (!pl->fused_begin) {
+    if (pl->fused_begin) {
+        // What is still queued: tasks whose class had its launch before they were queued. A chain is at most three
+        // tasks deep (variant -> reference allele -> begin pass) and all variant tasks are done by now, so after the
+        // first round every reference-allele task is done and after the second every begin task. Each launch drains its
+        // queue as a dynamic one (a continuation may append to the queue of the running launch); normally these launches
+        // find nothing (a few microseconds each).
+        sp.tasks = nullptr; sp.n_tasks_dev = nullptr; sp.n_tasks = 0;
+        for (int round = 0; round < 2; ++round)
+            for (size_t i = 0; i < pl->classes.size(); ++i) {
+                sp.queue_head = pl->counters.as<uint32_t>() + kCntFwdQueue + i;
+                set_dyn(i);
+                launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
+                note(kPhaseRev, (uint32_t)kClassR[pl->classes[i]]); mark(pl, ev, s);
+            }
+    } else {
         decide_kernel<<<(n_reads + tpb - 1) / tpb, tpb, 0, s>>>(dp);
         note(kPhaseDecide, 0); mark(pl, ev, s);
-    }
-
-    // begin launches over what is left in each class's queue (fused path: the tasks queued after their class's forward
-    // launch had run dry or finished; otherwise all of them)
-    sp.results = pl->rev.as<SwResult>(); sp.n_tasks = 0;
-    for (size_t i = 0; i < pl->classes.size(); ++i) {
-        sp.tasks = dp.rev_tasks + i * (size_t)nslots;
-        sp.n_tasks_dev = pl->counters.as<uint32_t>() + kCntRevReserve + i;
-        sp.queue_head = pl->counters.as<uint32_t>() + kCntRevQueue + i;
-        launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
-        note(kPhaseRev, (uint32_t)kClassR[pl->classes[i]]); mark(pl, ev, s);
+        // begin launches over the queues as static lists
+        sp.hook = nullptr; sp.group_remaining = nullptr;
+        sp.dyn_tasks = nullptr; sp.dyn_ready = nullptr; sp.dyn_head = nullptr; sp.dyn_reserve = nullptr;
+        sp.n_tasks = 0;
+        for (size_t i = 0; i < pl->classes.size(); ++i) {
+            sp.tasks = dp.rev_tasks + i * (size_t)pl->rev_capacity;
+            sp.n_tasks_dev = pl->counters.as<uint32_t>() + kCntRevReserve + i;
+            sp.queue_head = pl->counters.as<uint32_t>() + kCntRevQueue + i;
+            launch_class_idx(pl->classes[i], sp, grid_for(ctx, pl->classes[i]), s);
+            note(kPhaseRev, (uint32_t)kClassR[pl->classes[i]]); mark(pl, ev, s);
+        }
     }
 
     FinalParams fp;
@@ -1072,13 +1208,23 @@ extern "C" int nmsv_plan_download(nmsv_plan* pl, int32_t* checked, int32_t* supp
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     uint32_t cnt[kCntTotal];
+    unsigned long long cells[kCellsTotal];
     CUDA_TRY(ctx, cudaMemcpyAsync(cnt, pl->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(cells, pl->cells.p, sizeof(cells), cudaMemcpyDeviceToHost, s));
     if (supporting && pl->n_svs)
         CUDA_TRY(ctx, cudaMemcpyAsync(supporting, pl->supporting.p, sizeof(int32_t) * pl->n_svs, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
-    pl->stats.rev_tasks = 0;
-    for (uint32_t i = 0; i < 8; ++i) pl->stats.rev_tasks += cnt[kCntRevReserve + i];
-    pl->stats.d2h_bytes = sizeof(cnt) + sizeof(int32_t) * (uint64_t)pl->n_svs;
+    uint64_t queued = 0;
+    for (uint32_t i = 0; i < 8; ++i) queued += cnt[kCntRevReserve + i];
+    pl->stats.rev_tasks = queued - cells[kTasksSpawnedFwd];
+    pl->stats.fwd_tasks_queued = cells[kTasksSpawnedFwd];
+    pl->stats.cells_executed = pl->n_reads ? cells[kCellsFwd] : 0;
+    pl->stats.cells_begin = cells[kCellsBegin];
+    pl->stats.cells_pruned = pl->stats.cells_dedup - pl->stats.cells_executed;
+    pl->stats.d2h_bytes = sizeof(cnt) + sizeof(cells) + sizeof(int32_t) * (uint64_t)pl->n_svs;
+    if (cnt[kCntSaturated])
+        return set_err(ctx, NMSV_E_RANGE, "%u reads have an alignment whose score leaves the 16-bit range: parasail.ssw returns "
+                       "None there and the reference's ssw_check fails (count_sread_by_alignment.py:151)", cnt[kCntSaturated]);
     if (cnt[kCntStatus])
         return set_err(ctx, NMSV_E_INTERNAL, "%u begin-pass windows did not reproduce their forward score", cnt[kCntStatus]);
     if (checked) for (uint32_t i = 0; i < pl->n_svs; ++i) checked[i] = pl->checked[i];
@@ -1235,14 +1381,15 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     sp.codes = st.codes.as<uint8_t>(); sp.bnd = bnd.as<uint2>(); sp.bnd_stride = stride; sp.snap = (uint4*)ctx->snap;
     sp.match = sc->match; sp.mismatch = sc->mismatch; sp.open = sc->gap_open; sp.ext = sc->gap_extend;
     fill_packed(sp);
-    sp.tasks = tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = n_pairs; sp.results = fwd.as<SwResult>();
+    sp.tasks = tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = n_pairs;
+    sp.fwd_results = fwd.as<SwResult>(); sp.rev_results = rev.as<SwResult>();
     for (size_t i = 0; i < classes.size(); ++i) {
         sp.queue_head = counters.as<uint32_t>() + kCntFwdQueue + i;
         launch_class_idx(classes[i], sp, grid_for(ctx, classes[i]), s);
     }
     pair_decide_kernel<<<nb, tpb, 0, s>>>(pp);
     if (want_begin) {
-        sp.n_tasks = 0; sp.results = rev.as<SwResult>();
+        sp.n_tasks = 0;
         for (size_t i = 0; i < classes.size(); ++i) {
             sp.tasks = rev_tasks.as<SwTask>() + i * rev_cap;
             sp.n_tasks_dev = counters.as<uint32_t>() + kCntRevReserve + i;

@@ -67,8 +67,14 @@ __host__ __device__ constexpr int sw_bias(int open, int ext) { return open + (NM
 // 16-bit head-room a template needs on top of match * rows: the bias constant, one chunk of steps between two
 // rebases plus the unrolled body, and the row part of the bias. The host rejects longer templates (NMSV_E_RANGE).
 __host__ __device__ constexpr int sw_headroom(int open, int ext) { return sw_bias(open, ext) + ext + (kChunk + kUnroll + kMaxR) * ext; }
+// Largest true H the 16-bit lanes are allowed to hold: parasail's own limit (NULL when a score exceeds
+// INT16_MAX - match - 1) minus the head-room of the bias. A task whose scores cannot exceed match * min(rows, columns)
+// <= this cap needs no run-time check; any other task is watched once per 32 steps (H grows by at most `match` per
+// step) and reported as saturated (score -1, parasail: None) as soon as its maximum comes within 32 steps of the cap.
+__host__ __device__ constexpr int sw_score_cap(int match, int open, int ext) { return 32767 - match - 1 - sw_headroom(open, ext); }
 
-enum : uint32_t { kARev = 1u, kAComp = 2u, kBRev = 4u, kBComp = 8u, kCRev = 16u };
+enum : uint32_t { kARev = 1u, kAComp = 2u, kBRev = 4u, kBComp = 8u, kCRev = 16u,
+                  kTaskBegin = 32u };    // begin-pass task: result goes to rev_results and no continuation runs
 
 struct SwTask {          // 64 bytes
     uint64_t a_base;     // index into codes of row 0 of half A (row i is a_base +/- i)
@@ -90,7 +96,7 @@ struct SwTask {          // 64 bytes
 static_assert(sizeof(SwTask) == 64, "the dynamic queue reads a task as four 16-byte words");
 
 struct SwResult {        // [0] = half A, [1] = half B ; row/col 0-based in the task's own orientation
-    int32_t score[2];
+    int32_t score[2];    // -1: the 16-bit lanes could have saturated (parasail.ssw returns None)
     int32_t row[2];
     int32_t col[2];
 };
@@ -108,7 +114,9 @@ struct SwParams {
     const uint32_t* n_tasks_dev;   // when non-null the task count is read from device memory
     uint32_t n_tasks;
     uint32_t* queue_head;          // zeroed before the launch
-    SwResult* results;
+    SwResult* fwd_results;         // results of forward tasks (static or queued by the continuation)
+    SwResult* rev_results;         // results of begin-pass tasks (kTaskBegin)
+    unsigned long long* cells;     // optional: [0] += forward cells executed, [1] += begin-pass cells executed
     uint2* bnd;                    // [grid warps][bnd_stride] tile-boundary scratch (H, F of a tile's last row)
     uint32_t bnd_stride;
     uint4* snap;                   // [grid warps][kSnapWords * 32] column snapshots of the running-maximum tracker
@@ -123,7 +131,6 @@ struct SwParams {
     const uint32_t* dyn_ready;      //   dyn_ready[i] != 0; *dyn_head = next entry to hand out
     const uint32_t* dyn_reserve;
     uint32_t* dyn_head;
-    SwResult* dyn_results;
 };
 
 template <int R>
@@ -338,8 +345,14 @@ sw_wavefront_kernel(const SwParams p)
         const int rows = a_len > b_len ? a_len : b_len;
         const int ntiles = (rows + 32 * R - 1) / (32 * R);
         const int total_steps = (ncols + 31 + kUnroll - 1) & ~(kUnroll - 1);   // the step body is unrolled kUnroll x (pad steps are inert)
-        // steps the bias may run before the 16-bit lanes could overflow (host guarantees >= kChunk)
-        const int budget_steps = ext > 0 ? (32767 - bias - ext - p.match * rows) / ext - kMaxR - kUnroll : 0x7fffffff;
+        // steps the bias may run before the 16-bit lanes could overflow (>= kChunk by construction of the cap)
+        const int hbound = p.match * (rows < ncols ? rows : ncols);       // no alignment of this task can score more
+        const int hcap = sw_score_cap(p.match, p.open, ext);
+        const int hmax = hbound < hcap ? hbound : hcap;
+        const int budget_steps = ext > 0 ? (32767 - bias - ext - hmax) / ext - kMaxR - kUnroll : 0x7fffffff;
+        // run-time saturation watch (only tasks whose bound exceeds the cap can trip it)
+        const uint32_t sat_thr = hbound <= hcap ? 0xffffu : (uint32_t)(hcap - 32 * p.match);
+        uint32_t sat = 0;          // bit h: half h came within 32 steps of the cap
 
         // running best over tiles, per half: {score, col, row}
         int bs0 = 0, bc0 = 0, br0 = a_len - 1;
@@ -592,6 +605,10 @@ sw_wavefront_kernel(const SwParams p)
                         }
                         const uint32_t lift = wb - 0x00010001u;      // both halves >= bias >= 1: no borrow
                         bestprev = __vimax3_s16x2(bestprev, lift, lift);
+                        // true maxima so far (the running maximum sits at the row-0 bias of step g1-1; no borrow: it is
+                        // never below the floor). A parked half (unused B of a begin task) reads 255.
+                        const uint32_t tm = wb - (flb + (uint32_t)(g1 - 1) * p.ext2);
+                        sat |= ((tm & 0xffffu) > sat_thr ? 1u : 0u) | ((tm >> 16) > sat_thr ? 2u : 0u);
                     }
                     // ---- flush the staged boundary row of this group: entry q was produced at step g0+q for column
                     //      g0+q-31; remove its bias and store 32 columns with one coalesced 256-byte write
@@ -629,10 +646,12 @@ sw_wavefront_kernel(const SwParams p)
 
         if (lane == 0) {
             SwResult res;
-            res.score[0] = bs0; res.row[0] = br0; res.col[0] = bc0;
-            res.score[1] = b_len ? bs1 : 0; res.row[1] = br1; res.col[1] = bc1;
-            (src == 1 ? p.results : p.dyn_results)[task.out] = res;
-            if (src == 1 && p.hook) sw_task_done(p.hook, p.group_remaining, task.out);
+            res.score[0] = (sat & 1u) ? -1 : bs0; res.row[0] = br0; res.col[0] = bc0;
+            res.score[1] = b_len ? ((sat & 2u) ? -1 : bs1) : 0; res.row[1] = br1; res.col[1] = bc1;
+            const bool is_begin = task.flags & kTaskBegin;
+            (is_begin ? p.rev_results : p.fwd_results)[task.out] = res;
+            if (p.cells) atomicAdd(&p.cells[is_begin ? 1 : 0], (unsigned long long)(a_len + b_len) * (unsigned long long)ncols);
+            if (!is_begin && p.hook) sw_task_done(p.hook, p.group_remaining, task.out);
         }
     }
 }

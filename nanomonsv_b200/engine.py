@@ -5,6 +5,7 @@ Nothing here computes alignments; every method ends in a call into libnmsv_sw.so
 from __future__ import annotations
 
 import ctypes
+import weakref
 from dataclasses import dataclass
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -125,6 +126,7 @@ class Plan:
 
     def __init__(self, engine: "Engine", handle: ctypes.c_void_p, n_svs: int, n_reads: int):
         self._e, self._h, self.n_svs, self.n_reads = engine, handle, n_svs, n_reads
+        engine._plans.add(self)
 
     def run(self) -> None:
         self._e._check(self._e._L.nmsv_plan_run(self._h))
@@ -169,9 +171,12 @@ class Plan:
         return st.asdict()
 
     def close(self) -> None:
+        # the plan's buffers live on its engine's context and stream: an engine closes its plans before it goes away
+        # (Engine.close), so the handle is gone by then and this is a no-op
         if self._h:
             self._e._L.nmsv_plan_destroy(self._h)
             self._h = None
+            self._e._plans.discard(self)
 
     def __del__(self):
         try:
@@ -191,6 +196,7 @@ class Engine:
             raise EngineError(rc, (self._L.nmsv_last_error(None) or b"").decode())
         self._h = h
         self.device = int(device)
+        self._plans = weakref.WeakSet()      # live plans: destroyed before the context (they use its stream and pool)
 
     # ---- plumbing
     def _check(self, rc: int) -> None:
@@ -199,8 +205,14 @@ class Engine:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
+            for plan in list(self._plans):
+                plan.close()
             self._L.nmsv_destroy(self._h)
             self._h = None
+
+    def set_option(self, name: str, value: int) -> None:
+        """nmsv_set_option: "prune" = 0 computes every alignment the reference runs (parity tests)."""
+        self._check(self._L.nmsv_set_option(self._h, name.encode(), int(value)))
 
     def __enter__(self):
         return self
@@ -263,7 +275,18 @@ class Engine:
         return out
 
     # ---- stage seam
-    def plan(self, pack: SeqPack, svs: np.ndarray, reads: np.ndarray, scoring=DEFAULT_SCORING) -> Plan:
+    def plan(self, pack: SeqPack, svs: np.ndarray, reads: np.ndarray, scoring=DEFAULT_SCORING,
+             prune: Optional[bool] = None) -> Plan:
+        """prune=False: a plan that computes every alignment of the reference (download_alns then holds all tuples)."""
+        if prune is not None:
+            self.set_option("prune", 1 if prune else 0)
+        try:
+            return self._plan(pack, svs, reads, scoring)
+        finally:
+            if prune is not None:
+                self.set_option("prune", 1)
+
+    def _plan(self, pack: SeqPack, svs: np.ndarray, reads: np.ndarray, scoring=DEFAULT_SCORING) -> Plan:
         codes, offsets, lens = pack.finalize()
         svs = np.ascontiguousarray(svs, dtype=SV_DTYPE)
         reads = np.ascontiguousarray(reads, dtype=READ_DTYPE)

@@ -40,21 +40,22 @@ class SswResult:
 
 def ssw_batch(pairs: Sequence[Tuple[str, str]], open: int, extend: int, matrix: Matrix,
               engine: Optional[Engine] = None) -> List[Optional[SswResult]]:
-    """[(s1, s2), ...] -> results; None where parasail would return NULL (score not representable in 16 bits)."""
+    """[(s1, s2), ...] -> results; None where parasail returns NULL: the SCORE is not representable in 16 bits (the
+    engine reports that per pair as score1 = -1; the lengths of s1 and s2 do not matter, generate_consensus.py:119
+    passes whole reads as s1)."""
     eng = engine or default_engine()
     out: List[Optional[SswResult]] = [None] * len(pairs)
+    if not pairs:
+        return out
     pack = SeqPack(dedup=True)
-    t_idx, r_idx, where = [], [], []
-    limit = 32767 - matrix.match - 1 - (open + extend)
-    for i, (s1, s2) in enumerate(pairs):
+    t_idx, r_idx = [], []
+    for s1, s2 in pairs:
         if not s1 or not s2:
             raise ValueError("empty sequence")
-        if matrix.match * len(s1) > limit:
-            continue    # stays None
-        t_idx.append(pack.add(s1)); r_idx.append(pack.add(s2)); where.append(i)
-    if where:
-        res = eng.ssw_batch(pack, t_idx, r_idx, (matrix.match, matrix.mismatch, open, extend), want_begin=True)
-        for i, r in zip(where, res):
+        t_idx.append(pack.add(s1)); r_idx.append(pack.add(s2))
+    res = eng.ssw_batch(pack, t_idx, r_idx, (matrix.match, matrix.mismatch, open, extend), want_begin=True)
+    for i, r in enumerate(res):
+        if int(r["score1"]) >= 0:
             out[i] = SswResult(int(r["score1"]), int(r["ref_begin1"]), int(r["ref_end1"]), int(r["read_begin1"]),
                                int(r["read_end1"]))
     return out

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/nmsv.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert L.nmsv_abi_version() == 1
+    assert L.nmsv_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     assert _lib.ALN_DTYPE.itemsize == 24
     assert _lib.RECORD_DTYPE.itemsize == 104
     assert _lib.SSW_RESULT_DTYPE.itemsize == 20
-    assert ctypes.sizeof(_lib.Stats) == 72
+    assert ctypes.sizeof(_lib.Stats) == 112
 
 
 def test_encode_ascii_matches_python_lut():

@@ -152,13 +152,12 @@ def test_bias_rebase_on_very_long_reads(engine):
            (28000, 0, 13999, 9000, 22999)
 
 
-def test_longest_accepted_template_is_exact(engine):
-    """The host rejects templates whose scores could leave the 16-bit range including the kernel's bias head-room
-    (NMSV_E_RANGE, like parasail's None). The longest template it accepts forces a bias rebase at every chunk and must
-    still be exact; one base more must be refused, for every strip height."""
-    from nanomonsv_b200.engine import EngineError
+def test_no_length_limit_only_scores_saturate(engine):
+    """parasail.ssw returns None only when a SCORE leaves the 16-bit range, whatever the lengths. The kernel runs any
+    task whose bound match * min(rows, columns) fits below sw_score_cap unchecked (the longest such template forces a
+    bias rebase at every chunk and must be exact) and watches longer ones at run time."""
     rng = np.random.default_rng(17)
-    # match * len + headroom <= 32767 - match - 1 with headroom (nmsv_sw.cuh: sw_headroom) = bias (open + 7 * ext + 1)
+    # sw_score_cap = 32767 - match - 1 - headroom, headroom (nmsv_sw.cuh: sw_headroom) = bias (open + 7 * ext + 1)
     # + ext + (128 + 8 + 32) * ext = 180
     lmax = (32767 - 2 - 1 - 180) // 2
     tmpl = _rand(rng, lmax)
@@ -170,9 +169,19 @@ def test_longest_accepted_template_is_exact(engine):
            (2 * lmax, 0, lmax - 1, 700, 700 + lmax - 1)
     a = engine.ssw_check_batch(pack, [trc], [r])[0]
     assert (int(a["score"]), int(a["strand"]), int(a["qstart"]), int(a["qend"])) == (2 * lmax, -1, 1, lmax)
+    # longer templates: exact as long as the score stays below the cap ...
+    long_t = _rand(rng, 20000)
+    part = np.concatenate((_rand(rng, 300), long_t[4000:9000], _rand(rng, 500)))
+    unrelated = _rand(rng, 18000)
+    # ... and None (score1 = -1) when it does not: a 16 400-base perfect match scores 32 800 > 32 764
+    perfect = _rand(rng, 16400)
     pack = SeqPack()
-    t, r = pack.add_codes(_rand(rng, lmax + 1)), pack.add_codes(body)
-    with pytest.raises(EngineError) as e:
-        engine.ssw_batch(pack, [t], [r])
-    assert e.value.code == _lib.E_RANGE
+    ti, pi, ui, qi = pack.add_codes(long_t), pack.add_codes(part), pack.add_codes(unrelated), pack.add_codes(perfect)
+    res = engine.ssw_batch(pack, [ti, ti, qi, pi], [pi, ui, qi, ti])
+    codes, offsets, lens = pack.finalize()
+    exp, _ = O.ssw_batch(codes, offsets, lens, np.array([ti, ti, qi, pi]), np.array([pi, ui, qi, ti]), engine="striped")
+    for k in (0, 1, 3):
+        assert tuple(int(res[k][n]) for n in res.dtype.names) == tuple(int(exp[k][n]) for n in exp.dtype.names), k
+    assert int(res[0]["score1"]) > 8000
+    assert int(exp[2]["score1"]) == -1 and tuple(int(res[2][n]) for n in res.dtype.names) == (-1,) * 5
 

@@ -242,9 +242,41 @@ def test_errors_are_loud(engine):
     a = pack.add("ACGT")
     with pytest.raises(EngineError):
         engine.ssw_batch(pack, [a], [7])                 # index out of range
+    with pytest.raises(EngineError) as e:
+        engine.ssw_batch(pack, [a], [a], (100, -2, 3, 1))   # scoring parameters beyond the 16-bit lanes
+    assert e.value.code == _lib.E_RANGE
+    # a long template is no error: only a score that leaves the 16-bit range is, and then per pair (None)
     pack2 = SeqPack()
     big = pack2.add_codes(np.zeros(17000, dtype=np.uint8))
     rd = pack2.add("ACGT")
-    with pytest.raises(EngineError) as e:
-        engine.ssw_batch(pack2, [big], [rd])             # beyond the 16-bit range
-    assert e.value.code == _lib.E_RANGE
+    assert int(engine.ssw_batch(pack2, [big], [rd])[0]["score1"]) == 2
+
+
+def test_generate_paf_file_shape(engine):
+    """generate_consensus.generate_paf_file (reference generate_consensus.py:100-127) calls parasail.ssw(qseq, tseq, 3, 1,
+    M) with s1 = a WHOLE READ (10-50 kb) and s2 = the consensus (400-2000 b), and handles None per pair (:120-125).
+    The score is bounded by 2 * len(s2): no such pair may come back None, whatever len(s1) -- including the lengths
+    16 293 .. 16 380 that the round-1 length rule treated inconsistently."""
+    rnd = random.Random(91)
+    m = gpu_ssw.matrix_create("ACGT", 2, -2)
+    pairs = []
+    for n1 in (10000, 16293, 16300, 16380, 16381, 23000, 50000):
+        cons = "".join(rnd.choice("ACGT") for _ in range(rnd.choice((400, 900, 2000))))
+        body = _mutated_copy(rnd, cons, 0.08)
+        at = rnd.randrange(0, n1 - len(body))
+        read = "".join(rnd.choice("ACGT") for _ in range(at)) + body
+        read += "".join(rnd.choice("ACGT") for _ in range(n1 - len(read)))
+        pairs.append((read, cons))
+        pairs.append((O.reverse_complement(read), cons))        # unrelated strand: a low score, still a result
+    got = gpu_ssw.ssw_batch(pairs, 3, 1, m, engine=engine)
+    for (s1, s2), g in zip(pairs, got):
+        e = O.ssw(s1, s2, engine="striped")
+        assert g is not None and e is not None
+        assert (g.score1, g.read_begin1, g.read_end1, g.ref_begin1, g.ref_end1) == e.astuple(), (len(s1), len(s2))
+    assert sum(1 for g in got if g.score1 > 500) == len(pairs) // 2
+    # long against long: a result while the score is representable, None once it is not (like the oracle / parasail)
+    a = "".join(rnd.choice("ACGT") for _ in range(17000))
+    b = "".join(rnd.choice("ACGT") for _ in range(19000))
+    g = gpu_ssw.ssw(a, b, 3, 1, m, engine=engine)
+    assert g is not None and (g.score1, g.read_begin1, g.read_end1, g.ref_begin1, g.ref_end1) == O.ssw(a, b, engine="striped").astuple()
+    assert gpu_ssw.ssw(a, a, 3, 1, m, engine=engine) is None and O.ssw(a, a, engine="striped") is None

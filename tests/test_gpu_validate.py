@@ -99,12 +99,13 @@ def test_all_alignment_tuples_of_all_reads(engine):
                               short_fraction=0.7)
     wl = synth.make_workload(cfg)
     pack, svs, reads = wl.to_batch("tumor", var_read_min_mapq=0)
-    plan = engine.plan(pack, svs, reads)
+    plan = engine.plan(pack, svs, reads, prune=False)      # every alignment the reference runs
     plan.run()
     checked, supporting, records = plan.download()
     alns, flags = plan.download_alns()
     st = plan.stats()
-    assert st["cells_executed"] <= st["cells_reference"] and st["fwd_tasks"] > 0
+    assert st["cells_executed"] == st["cells_dedup"] <= st["cells_reference"] and st["fwd_tasks"] > 0
+    assert st["cells_pruned"] == 0 and st["reads_pruned"] == 0
     codes, offsets, lens = pack.finalize()
 
     def seq(i):
@@ -137,6 +138,25 @@ def test_all_alignment_tuples_of_all_reads(engine):
     c2, s2, r2 = plan.download()
     assert (s2 == supporting).all() and (r2 == records).all()
     plan.close()
+    # the default plan skips alignments that cannot change an output: same counts and records, fewer cells; what it
+    # did compute equals the full plan's tuples, a pruned read (flag 4) has none
+    plan = engine.plan(pack, svs, reads)
+    plan.run()
+    c3, s3, r3 = plan.download()
+    alns3, flags3 = plan.download_alns()
+    st3 = plan.stats()
+    plan.close()
+    assert (c3 == checked).all() and (s3 == supporting).all() and (r3 == records).all()
+    assert st3["cells_executed"] + st3["cells_pruned"] == st3["cells_dedup"] == st["cells_dedup"]
+    assert 0 < st3["cells_executed"] < st["cells_executed"] and st3["reads_pruned"] > 0
+    assert st3["reads_pruned"] == int(((flags3 & 4) != 0).sum())
+    assert ((flags3 & 3) == (flags & 3)).all()
+    for r in range(len(reads)):
+        for s in range(4):
+            if alns3[r, s]["strand"] != 0:
+                assert alns3[r, s] == alns[r, s]
+            if flags3[r] & 4:
+                assert alns3[r, s]["strand"] == 0 and alns3[r, s]["score"] == 0
 
 
 def test_edge_cases(engine, tmp_path):
@@ -205,16 +225,48 @@ def test_fused_and_separate_begin_pass_agree(engine, monkeypatch):
         out = {}
         for mode in ("1", "0"):
             monkeypatch.setenv("NMSV_FUSED_BEGIN", mode)
-            plan = engine.plan(pack, svs, reads)
-            for _ in range(2):
-                plan.run()
-            checked, supporting, records = plan.download()
-            alns, flags = plan.download_alns()
-            st = plan.stats()
-            assert st["kernel_launches"] == (2 if mode == "1" else 3) + 2 * st["n_classes"]
-            out[mode] = (checked, supporting, records, alns, flags, st["rev_tasks"])
-            plan.close()
-        a, b = out["1"], out["0"]
+            for prune in (False, True):
+                plan = engine.plan(pack, svs, reads, prune=prune)
+                for _ in range(2):
+                    plan.run()
+                checked, supporting, records = plan.download()
+                alns, flags = plan.download_alns()
+                st = plan.stats()
+                assert st["kernel_launches"] == (2 + 3 * st["n_classes"] if mode == "1" else 3 + 2 * st["n_classes"])
+                out[mode, prune] = (checked, supporting, records, alns, flags, st["rev_tasks"])
+                plan.close()
+        a, b = out["1", False], out["0", False]
         assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (a[2] == b[2]).all()
         assert (a[3] == b[3]).all() and (a[4] == b[4]).all() and a[5] == b[5] > 0
         assert int(a[1].sum()) > 0
+        for key in (("1", True), ("0", True)):      # pruned plans: same counts, records and begin tasks
+            c = out[key]
+            assert (a[0] == c[0]).all() and (a[1] == c[1]).all() and (a[2] == c[2]).all() and a[5] == c[5]
+
+
+def test_pruning_never_changes_an_output(engine):
+    """nmsv_set_option("prune"): reads whose mapq test fails are only counted and ref1/ref2 are aligned only for reads
+    that pass the variant tests (reference :336-346, :384-389). Counts and records must equal the unpruned plan's on
+    every workload shape, with and without a mapq threshold."""
+    shapes = (("testdata_shaped", dict(n_sv=12, coverage=9.0, short_fraction=0.7, seed=411), 200),
+              ("colo829_shaped", dict(n_sv=6, coverage=7.0, seed=412, validate_sequence_length=600), 600),
+              ("single_breakend", dict(n_sv=10, coverage=9.0, seed=413, sbnd_contig_range=(100, 900),
+                                       sbnd_tail_range=(2000, 7000)), 200))
+    for preset, kw, L in shapes:
+        cfg = dataclasses.replace(synth.PRESETS[preset], read_len_mean=2500, read_len_min=600, read_len_max=7000,
+                                  contig_len=150000, n_contigs=2, **kw)
+        wl = synth.make_workload(cfg)
+        for sample in ("tumor", "control"):
+            for min_mapq in (0, 40):
+                pack, svs, reads = wl.to_batch(sample, var_read_min_mapq=min_mapq)
+                res = {}
+                for prune in (False, True):
+                    plan = engine.plan(pack, svs, reads, prune=prune)
+                    plan.run()
+                    res[prune] = plan.download() + (plan.stats(),)
+                    plan.close()
+                full, fast = res[False], res[True]
+                assert (full[0] == fast[0]).all() and (full[1] == fast[1]).all() and (full[2] == fast[2]).all()
+                assert fast[3]["cells_executed"] <= full[3]["cells_executed"]
+                if sample == "tumor":
+                    assert int(full[1].sum()) > 0

@@ -22,5 +22,6 @@ for _ in range(3):
     plan.run(); torch.cuda.synchronize()
     kt = plan.kernel_times()
     best = min(best, [ms for n_, r, ms in kt if n_ == "sw_forward"][0])
+plan.download()
 st = plan.stats()
-print(os.environ.get("NMSV_LIB_PATH"), "fwd_ms", round(best, 2), "gcups_exec", round(st["cells_executed"] / best / 1e6))
+print(os.environ.get("NMSV_PRUNE"), os.environ.get("NMSV_SPAWN_FIRST"), n, os.environ.get("NMSV_LIB_PATH"), "fwd_ms", round(best, 2), "gcups_exec", round(st["cells_executed"] / best / 1e6))
