@@ -100,7 +100,7 @@ static int set_err(const nmsv_ctx* ctx, int code, const char* fmt, ...)
 template <int R>
 static cudaError_t setup_class(int* blocks_per_sm)
 {
-    const size_t smem = kWarpsPerBlock * warp_smem_bytes<R>();
+    const size_t smem = block_smem_bytes<R>();
     cudaError_t e = cudaFuncSetAttribute(sw_wavefront_kernel<R, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(sw_wavefront_kernel<R, -1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -131,7 +131,7 @@ static cudaError_t setup_class_idx(int cls, int* bps)
 template <int R>
 static void launch_class(const SwParams& p, int grid, cudaStream_t s)
 {
-    const size_t smem = kWarpsPerBlock * warp_smem_bytes<R>();
+    const size_t smem = block_smem_bytes<R>();
     if (p.open == 3 && p.ext == 1)      // the reference's gap penalties: instantiation with immediate operands
         sw_wavefront_kernel<R, 3, 1><<<grid, kWarpsPerBlock * 32, smem, s>>>(p);
     else
@@ -835,11 +835,12 @@ static int grid_for(const nmsv_ctx* ctx, int cls)
     return ctx->prop.multiProcessorCount * std::max(1, ctx->blocks_per_sm[cls]);
 }
 
-static int max_grid_warps(const nmsv_ctx* ctx)
+// global boundary buffers: kGBufs per block, only needed by tasks with more tiles than a block has warps
+static int max_grid_gbufs(const nmsv_ctx* ctx)
 {
     int g = 0;
     for (int c = 0; c < kNumClasses; ++c) g = std::max(g, grid_for(ctx, c));
-    return g * kWarpsPerBlock;
+    return g * kGBufs;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -981,7 +982,7 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
             const int cls = choose_class((uint32_t)m);
             const uint32_t nt = tiles_of((uint32_t)m, cls);
             stt.cells_dedup += 2 * m * n;
-            if (nt > 1) max_cols_multi = std::max<uint32_t>(max_cols_multi, (uint32_t)n);
+            if (nt > (uint32_t)kW) max_cols_multi = std::max<uint32_t>(max_cols_multi, (uint32_t)n);
             if (pruned) continue;
             if (pl->lazy_refs && s >= NMSV_SLOT_REF1) { spawner = true; continue; }      // queued on the device, if at all
             stt.cells_padded += 2ull * nt * 32 * kClassR[cls] * (n + 31);
@@ -1033,7 +1034,7 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
     CUDA_TRY(ctx, pl->records.alloc(sizeof(nmsv_record) * (uint64_t)n_reads, s));
     CUDA_TRY(ctx, pl->counters.alloc(sizeof(uint32_t) * kCntTotal, s));
     pl->bnd_stride = max_cols_multi ? max_cols_multi : 1;
-    const uint64_t bnd_bytes = max_cols_multi ? (uint64_t)max_grid_warps(ctx) * pl->bnd_stride * sizeof(uint2) : 16;
+    const uint64_t bnd_bytes = max_cols_multi ? (uint64_t)max_grid_gbufs(ctx) * pl->bnd_stride * sizeof(uint2) : 16;
     CUDA_TRY(ctx, pl->bnd.alloc(bnd_bytes, s));
     stt.workspace_bytes = pl->tasks.bytes + pl->fwd.bytes + pl->rev_tasks.bytes + pl->rev_ready.bytes +
                           pl->group_remaining.bytes + pl->rev.bytes + pl->sel.bytes +
@@ -1328,7 +1329,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
         const int c = choose_class(lens[tmpl_idx[i]]);
         st.cls_host[tmpl_idx[i]] = (uint8_t)kClassR[c];
         class_used[c] = true;
-        if (tiles_of(lens[tmpl_idx[i]], c) > 1) max_cols_multi = std::max(max_cols_multi, lens[read_idx[i]]);
+        if (tiles_of(lens[tmpl_idx[i]], c) > (uint32_t)kW) max_cols_multi = std::max(max_cols_multi, lens[read_idx[i]]);
     }
     std::vector<int> classes;
     for (int c = 0; c < kNumClasses; ++c) if (class_used[c]) classes.push_back(c);
@@ -1356,7 +1357,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     CUDA_TRY(ctx, counters.alloc(sizeof(uint32_t) * kCntTotal, s));
     CUDA_TRY(ctx, cudaMemsetAsync(counters.p, 0, sizeof(uint32_t) * kCntTotal, s));
     const uint32_t stride = max_cols_multi ? max_cols_multi : 1;
-    CUDA_TRY(ctx, bnd.alloc(max_cols_multi ? (uint64_t)max_grid_warps(ctx) * stride * sizeof(uint2) : 16, s));
+    CUDA_TRY(ctx, bnd.alloc(max_cols_multi ? (uint64_t)max_grid_gbufs(ctx) * stride * sizeof(uint2) : 16, s));
     const size_t out_bytes = out_ssw ? sizeof(nmsv_ssw_result) * (size_t)n_pairs : sizeof(nmsv_aln) * (size_t)n_pairs;
     CUDA_TRY(ctx, d_out.alloc(out_bytes, s));
 

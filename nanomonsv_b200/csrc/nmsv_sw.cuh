@@ -12,8 +12,11 @@
 //     wavefront); H and F of a strip's last row go to lane l+1 with two __shfl_up_sync per step.
 //   * the substitution scores come from a per-warp shared-memory profile prof[code][row] (LDS.128, conflict
 //     free) so the inner loop has no compares; the read is staged through a shared-memory ring.
-//   * templates longer than one tile run tile after tile; the H/F row between two tiles goes through a per-warp
-//     global scratch that stays L2 resident (8 B per column).
+//   * templates longer than one tile: the tiles of a task are JOBS that the warps of one block claim in order, so the
+//     tiles of a task run side by side on different warps, each lagging its producer by two 32-column groups; the H/F
+//     row between two tiles is handed over through a 128-column shared-memory ring with two progress counters
+//     (no global round trip, no scratch that grows with the read, and the serial chain of a task is one tile, not
+//     all of them). Only tasks with more tiles than a block has warps spill every fourth boundary row to global.
 //   * every stored value of (step t, strip row k) is  true value + a + (t - tbase + k) * ext  -- an anti-diagonal
 //     bias: a value that moves one column to the right (E) or one row down (F) meets a bias that is ext larger,
 //     so BOTH gap extensions cost no instruction; the zero floor of local alignment becomes a sliding window of
@@ -133,6 +136,38 @@ struct SwParams {
     uint32_t* dyn_head;
 };
 
+// ---- block-level job scheduler (shared memory) ------------------------------------------------------------------------
+// A job = one tile (32*R rows) of one task over all columns. The warps of a block claim jobs in sequence (tile after tile
+// of a task, task after task from the global lists); tile j+1 consumes the last row (H, F per column) of tile j through
+// a link: a shared-memory ring with `produced` / `consumed` column counters, or -- for the link into every kW-th job of a
+// task with more than kW tiles, whose consumer can only be claimed a whole tile later -- one of two global buffers.
+constexpr int kW = kWarpsPerBlock;
+constexpr int kSlots = kW + 2;         // tasks in flight per block (at most kW running jobs + the task being dealt out)
+constexpr int kRings = kW + 1;         // live ring links <= kW - 1 running consumers + the claimed job's in- and out-link
+constexpr int kRingCols = 128;         // columns per ring; a consumer lags its producer by 2..5 groups of 32 columns
+constexpr int kGBufs = 2;              // global boundary buffers per block
+constexpr uint32_t kNoLink = 0xfu;
+constexpr uint32_t kJobQuit = 0xffffffffu, kJobRetry = 0xfffffffeu;
+
+struct alignas(16) Slot {              // one task in flight in this block (the task is read as 16-byte words)
+    SwTask task;
+    uint32_t ntiles, next_tile, tiles_done, sat;
+    uint32_t lb[2];                    // per half: a score some cell of the task is known to reach (lower bound of the result)
+    int32_t best_s[2], best_c[2], best_r[2];
+    uint32_t last_out;                 // out-link of the tile claimed last = in-link of the next one
+    uint32_t pad_;
+};
+
+struct LinkCtl { uint32_t produced, consumed; };     // columns [0, produced) written / [0, consumed) no longer needed
+
+struct BlockCtl {
+    uint32_t lock, quit, n_waiting, cur;             // cur = slot whose tiles are being dealt out (kSlots = none)
+    uint32_t slot_busy, ring_busy, gbuf_busy, seq;   // seq = sequence number of the next job
+    LinkCtl links[kRings + kGBufs];
+    Slot slots[kSlots];
+};
+constexpr size_t kCtlBytes = (sizeof(BlockCtl) + 127) & ~(size_t)127;
+
 template <int R>
 __host__ __device__ constexpr int groups_of() { return (R + 3) / 4; }
 
@@ -140,11 +175,17 @@ template <int R>
 __host__ __device__ constexpr size_t warp_smem_bytes()
 {
     return (size_t)kNumCodes * groups_of<R>() * 32 * 16   // profile, uint4 [code][group][lane]
-         + (size_t)kChunk * 8                               // boundary ring (inputs of lane 0), uint2 per column
+         + (size_t)32 * 8                                   // boundary inputs of lane 0 for one group of 32 columns, biased
          + (size_t)32 * 8                                   // boundary staging (outputs of lane 31), one group
          + (size_t)16                                       // constant slot read by lanes 1..31 instead of the ring
          + (size_t)16                                       // mbarrier of the TMA (cp.async.bulk) read staging
          + (size_t)2 * kRing;                               // read ring (4 chunk slots), stored twice (mirrored)
+}
+
+template <int R>
+__host__ __device__ constexpr size_t block_smem_bytes()
+{
+    return kCtlBytes + (size_t)kRings * kRingCols * 8 + (size_t)kWarpsPerBlock * warp_smem_bytes<R>();
 }
 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi)
@@ -224,35 +265,164 @@ __device__ __forceinline__ void warp_argbest(int& s, int& c, int& r)
     }
 }
 
-// Task acquisition, kept out of line: its data-dependent loops would otherwise cost the kernel body the compiler's
-// convergence analysis (BRA.DIV before every shuffle of the hot loop). Nothing here waits for work to appear: a warp
-// that finds both queues empty leaves, and whatever is queued later is run by the follow-up launch over the same queue.
-__device__ __noinline__ uint32_t sw_pick_task(uint32_t* queue_head, uint32_t n_tasks, uint32_t* dyn_head,
-                                           const uint32_t* dyn_reserve, const uint32_t* dyn_ready)
+// ---- links ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+__device__ __forceinline__ unsigned long long global_ns()
 {
-    uint32_t src = 0, ti = 0;
-    if ((threadIdx.x & 31) == 0) {
-        if (dyn_reserve) {
-            uint32_t h = *reinterpret_cast<volatile uint32_t*>(dyn_head);
-            while (h < *reinterpret_cast<const volatile uint32_t*>(dyn_reserve)) {
-                const uint32_t o = atomicCAS(dyn_head, h, h + 1u);
-                if (o == h) { src = 2; ti = h; break; }
-                h = o;
-            }
-            // the producer publishes dyn_ready[ti] right after the task body (fence in between); it is a running warp
-            // between two adjacent statements, so this wait is a few hundred nanoseconds at most
-            if (src == 2) {
-                while (*reinterpret_cast<const volatile uint32_t*>(dyn_ready + ti) == 0u) __nanosleep(64);
-                __threadfence();
-            }
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// A wait on another warp of the same block ends when that warp gets on with its tile; no legitimate wait comes near this
+// bound (a whole 1 Mb read against a tile takes well under a second). Trapping turns a scheduling bug into an error
+// return of the C ABI instead of a hung device.
+constexpr unsigned long long kWatchdogNs = 20ull * 1000 * 1000 * 1000;
+
+__device__ __noinline__ void link_wait_slow(const uint32_t* flag, uint32_t need)
+{
+    const unsigned long long t0 = global_ns();
+    while ((int32_t)(ld_vol(flag) - need) < 0) {
+        __nanosleep(40);
+        if (global_ns() - t0 > kWatchdogNs) __trap();
+    }
+}
+
+// wait until *flag >= need (a column count written by another warp of this block). The common case -- the other side
+// is far enough along -- is one shared-memory load and a vote; the poll loop is kept out of line (a data-dependent
+// loop inlined into the kernel body costs the compiler its convergence analysis of the hot loop).
+__device__ __forceinline__ void link_wait(const uint32_t* flag, uint32_t need)
+{
+    if (__any_sync(kFull, (int32_t)(ld_vol(flag) - need) < 0)) link_wait_slow(flag, need);
+    __threadfence_block();
+}
+
+__device__ __forceinline__ void ctl_lock(BlockCtl* c)
+{
+    const unsigned long long t0 = global_ns();
+    while (atomicCAS(&c->lock, 0u, 1u) != 0u) {
+        __nanosleep(20);
+        if (global_ns() - t0 > kWatchdogNs) __trap();
+    }
+    __threadfence_block();
+}
+
+__device__ __forceinline__ void ctl_unlock(BlockCtl* c)
+{
+    __threadfence_block();
+    atomicExch(&c->lock, 0u);
+}
+
+// Next task of this launch for the calling block (lane 0 of some warp, holding the block lock): the dynamic queue first
+// (tasks queued by continuations: reference-allele alignments and begin passes of reads that are already decided), then
+// the static list. Returns false when both are empty right now.
+__device__ __forceinline__ bool pick_task(const SwParams& p, uint32_t n_tasks, SwTask& task)
+{
+    const SwTask* at = nullptr;
+    if (p.dyn_reserve) {
+        uint32_t h = ld_vol(p.dyn_head);
+        while (h < ld_vol(p.dyn_reserve)) {
+            const uint32_t o = atomicCAS(p.dyn_head, h, h + 1u);
+            if (o == h) { at = p.dyn_tasks + h; break; }
+            h = o;
         }
-        if (!src) {
-            ti = atomicAdd(queue_head, 1u);
-            if (ti < n_tasks) src = 1;
+        // the producer publishes dyn_ready[h] right after the task body (fence in between); it is a running warp
+        // between two adjacent statements, so this wait is a few hundred nanoseconds at most
+        if (at) {
+            while (ld_vol(p.dyn_ready + h) == 0u) __nanosleep(64);
+            __threadfence();
         }
     }
-    __syncwarp();
-    return src == 0 ? 0xffffffffu : (src == 2 ? (ti | 0x80000000u) : ti);
+    if (!at && ld_vol(p.queue_head) < n_tasks) {      // (checked first: idle warps poll, the counter must not wrap)
+        const uint32_t ti = atomicAdd(p.queue_head, 1u);
+        if (ti < n_tasks) at = p.tasks + ti;
+    }
+    if (!at) return false;
+    // through L2 (a line of the dynamic queue may be stale in L1)
+    const uint4* q = reinterpret_cast<const uint4*>(at);
+    const uint4 w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2), w3 = __ldcg(q + 3);
+    task.a_base = ((uint64_t)w0.y << 32) | w0.x; task.b_base = ((uint64_t)w0.w << 32) | w0.z;
+    task.c_base = ((uint64_t)w1.y << 32) | w1.x; task.a_len = w1.z; task.b_len = w1.w;
+    task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w; task.best0 = w3.x;
+    return true;
+}
+
+// Claim the next job of this block (lane 0). Returns slot | tile << 4 | in-link << 24 | out-link << 28, or kJobQuit.
+// A warp that finds nothing to claim waits while another warp of its block is still running (the continuation of that
+// warp's task may queue new tasks, and the tiles of a multi-tile task need all the warps of the block); the block
+// leaves when all its warps wait at once and both lists are empty. Tasks queued later by other blocks are run by
+// those blocks themselves, or by the follow-up launches over the same queue.
+__device__ __noinline__ uint32_t claim_job(BlockCtl* ctl, const SwParams& p, uint32_t n_tasks, uint32_t R)
+{
+    bool counted = false;
+    for (;;) {
+        ctl_lock(ctl);
+        uint32_t ret = kJobRetry;
+        if (ctl->quit) ret = kJobQuit;
+        else {
+            if (ctl->cur == (uint32_t)kSlots) {
+                SwTask task;
+                task.pad_[0] = task.pad_[1] = task.pad_[2] = 0;
+                if (pick_task(p, n_tasks, task)) {
+                    if (task.rclass == R && task.ncols != 0) {
+                        const uint32_t si = (uint32_t)__ffs((int)~ctl->slot_busy) - 1u;      // a free slot exists (kSlots > kW)
+                        ctl->slot_busy |= 1u << si;
+                        Slot& s = ctl->slots[si];
+                        s.task = task;
+                        const uint32_t rows = task.a_len > task.b_len ? task.a_len : task.b_len;
+                        s.ntiles = (rows + 32u * R - 1u) / (32u * R);
+                        s.next_tile = 0; s.tiles_done = 0; s.sat = 0;
+                        // begin pass: the score is known (only cells that reach it matter); its unused half B holds the
+                        // floor everywhere, park its bound out of reach so that it never takes the exact path
+                        s.lb[0] = task.best0; s.lb[1] = task.b_len ? 0u : 256u;
+                        s.best_s[0] = (int32_t)task.best0; s.best_c[0] = task.best0 ? 0x7fffffff : 0;
+                        s.best_r[0] = task.best0 ? 0x7fffffff : (int32_t)task.a_len - 1;
+                        s.best_s[1] = 0; s.best_c[1] = 0; s.best_r[1] = (int32_t)task.b_len - 1;
+                        s.last_out = kNoLink;
+                        ctl->cur = si;
+                        // ring links never cross a multiple of kW in the job sequence: a task of up to kW tiles is not
+                        // split over such a boundary, longer ones start on one
+                        const uint32_t ph = ctl->seq % (uint32_t)kW;
+                        if (ph && (s.ntiles > (uint32_t)kW || ph + s.ntiles > (uint32_t)kW)) ctl->seq += (uint32_t)kW - ph;
+                    }
+                    // (a task of another strip class, or an empty one, is skipped; look again without sleeping)
+                    else { ctl_unlock(ctl); continue; }
+                } else {
+                    if (!counted) { counted = true; ctl->n_waiting += 1u; }
+                    if (ctl->n_waiting == (uint32_t)kW) { ctl->quit = 1u; ret = kJobQuit; }
+                }
+            }
+            if (ctl->cur != (uint32_t)kSlots) {
+                Slot& s = ctl->slots[ctl->cur];
+                const uint32_t j = s.next_tile;
+                uint32_t out = kNoLink;
+                bool ok = true;
+                if (j + 1u < s.ntiles) {
+                    if ((ctl->seq + 1u) % (uint32_t)kW == 0u) {          // the consumer is claimed a tile later: global link
+                        const uint32_t freeg = ~ctl->gbuf_busy & ((1u << kGBufs) - 1u);
+                        if (freeg) { out = (uint32_t)kRings + (uint32_t)__ffs((int)freeg) - 1u; ctl->gbuf_busy |= 1u << (out - kRings); }
+                        else ok = false;                                 // both in use: their consumers are running, retry
+                    } else {
+                        out = (uint32_t)__ffs((int)~ctl->ring_busy) - 1u;    // a free ring exists (kRings = kW + 1)
+                        ctl->ring_busy |= 1u << out;
+                    }
+                }
+                if (ok) {
+                    ret = ctl->cur | (j << 4) | (s.last_out << 24) | (out << 28);
+                    if (out != kNoLink) { ctl->links[out].produced = 0u; ctl->links[out].consumed = 0u; }
+                    s.last_out = out;
+                    s.next_tile = j + 1u;
+                    ctl->seq += 1u;
+                    if (s.next_tile == s.ntiles) ctl->cur = (uint32_t)kSlots;
+                    if (counted) { counted = false; ctl->n_waiting -= 1u; }
+                }
+            }
+        }
+        ctl_unlock(ctl);
+        if (ret != kJobRetry) return ret;
+        __nanosleep(500);
+    }
 }
 
 // lane 0, after the result of a static task is stored: count the task's group down and run the continuation when
@@ -266,6 +436,47 @@ __device__ __noinline__ void sw_task_done(const GroupHook* hook, uint32_t* group
     }
 }
 
+// lane 0, at the end of a tile: merge the tile's best cells into the task's result (higher score, then smaller column,
+// then smaller row -- parasail's end cell), release the tile's in-link, and when this was the task's last tile to finish
+// store the result and run the continuation.
+__device__ __noinline__ void finish_job(BlockCtl* ctl, const SwParams& p, uint32_t code, int s0, int c0, int r0,
+                                        int s1, int c1, int r1, uint32_t sat)
+{
+    const uint32_t si = code & 15u, in_link = (code >> 24) & 15u;
+    Slot& s = ctl->slots[si];
+    ctl_lock(ctl);
+    if (s0 > 0 && (s0 > s.best_s[0] || (s0 == s.best_s[0] && (c0 < s.best_c[0] || (c0 == s.best_c[0] && r0 < s.best_r[0]))))) {
+        s.best_s[0] = s0; s.best_c[0] = c0; s.best_r[0] = r0;
+    }
+    if (s1 > 0 && (s1 > s.best_s[1] || (s1 == s.best_s[1] && (c1 < s.best_c[1] || (c1 == s.best_c[1] && r1 < s.best_r[1]))))) {
+        s.best_s[1] = s1; s.best_c[1] = c1; s.best_r[1] = r1;
+    }
+    s.sat |= sat;
+    if (in_link != kNoLink) {
+        if (in_link < (uint32_t)kRings) ctl->ring_busy &= ~(1u << in_link);
+        else ctl->gbuf_busy &= ~(1u << (in_link - (uint32_t)kRings));
+    }
+    s.tiles_done += 1u;
+    const bool done = s.tiles_done == s.ntiles;
+    SwResult res;
+    uint32_t out = 0, flags = 0;
+    unsigned long long cells = 0;
+    if (done) {
+        res.score[0] = (s.sat & 1u) ? -1 : s.best_s[0]; res.row[0] = s.best_r[0]; res.col[0] = s.best_c[0];
+        res.score[1] = s.task.b_len ? ((s.sat & 2u) ? -1 : s.best_s[1]) : 0; res.row[1] = s.best_r[1]; res.col[1] = s.best_c[1];
+        out = s.task.out; flags = s.task.flags;
+        cells = (unsigned long long)(s.task.a_len + s.task.b_len) * (unsigned long long)s.task.ncols;
+        ctl->slot_busy &= ~(1u << si);
+    }
+    ctl_unlock(ctl);
+    if (!done) return;
+    const bool is_begin = flags & kTaskBegin;
+    (is_begin ? p.rev_results : p.fwd_results)[out] = res;
+    if (p.cells) atomicAdd(&p.cells[is_begin ? 1 : 0], cells);
+    if (!is_begin && p.hook) sw_task_done(p.hook, p.group_remaining, out);
+}
+
+
 // OPEN/EXT >= 0: gap penalties known at compile time (the reference always calls parasail.ssw(.., 3, 1, ..),
 // count_sread_by_alignment.py:148): the DPX add operands become immediates, which saves one vector-register read on
 // two of the four DPX instructions per cell pair. OPEN = EXT = -1: generic instantiation, operands from the parameters.
@@ -277,15 +488,17 @@ sw_wavefront_kernel(const SwParams p)
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    uint8_t* wbase = smem_raw + (size_t)warp * warp_smem_bytes<R>();
+    BlockCtl* const ctl = reinterpret_cast<BlockCtl*>(smem_raw);
+    uint2* const rings = reinterpret_cast<uint2*>(smem_raw + kCtlBytes);               // [kRings][kRingCols]
+    uint8_t* wbase = smem_raw + kCtlBytes + (size_t)kRings * kRingCols * 8 + (size_t)warp * warp_smem_bytes<R>();
     uint4* prof = reinterpret_cast<uint4*>(wbase);
     uint2* bring = reinterpret_cast<uint2*>(wbase + (size_t)kNumCodes * G * 32 * 16);
-    uint2* bstage = bring + kChunk;
+    uint2* bstage = bring + 32;
     uint2* bconst = bstage + 32;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bconst + 2);
     uint8_t* rring = reinterpret_cast<uint8_t*>(bconst + 4);
     const uint32_t gwarp = blockIdx.x * kWarpsPerBlock + warp;
-    uint2* const bnd0 = p.bnd + (size_t)gwarp * p.bnd_stride;
+    uint2* const gbuf0 = p.bnd + (size_t)blockIdx.x * kGBufs * p.bnd_stride;          // [kGBufs][bnd_stride]
     uint4* const snap_lane = p.snap + (size_t)gwarp * (kSnapWords * 32) + lane;    // word w of half h: [(h * (G+1) + w) * 32]
 
     const uint32_t n_tasks = p.n_tasks_dev ? *p.n_tasks_dev : p.n_tasks;
@@ -320,30 +533,36 @@ sw_wavefront_kernel(const SwParams p)
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncwarp();
+    if (threadIdx.x == 0) {
+        ctl->lock = 0; ctl->quit = 0; ctl->n_waiting = 0; ctl->cur = (uint32_t)kSlots;
+        ctl->slot_busy = ~((1u << kSlots) - 1u); ctl->ring_busy = ~((1u << kRings) - 1u); ctl->gbuf_busy = 0; ctl->seq = 0;
+    }
+    __syncthreads();               // the only block-wide barrier: from here on the warps meet through the links only
     uint32_t tma_parity = 0;       // phase of the next mbarrier completion to wait for
 
     for (;;) {
-        // ---- next task: the dynamic queue first (begin tasks of reads that are already decided), then the static list
-        uint32_t code = sw_pick_task(p.queue_head, n_tasks, p.dyn_head, p.dyn_reserve, p.dyn_ready);
+        // ---- next job: a tile of the task this block is dealing out, or the first tile of a new task
+        uint32_t code = 0;
+        if (lane == 0) code = claim_job(ctl, p, n_tasks, (uint32_t)R);
         code = __shfl_sync(kFull, code, 0);
-        if (code == 0xffffffffu) break;
-        const uint32_t src = (code >> 31) + 1u, ti = code & 0x7fffffffu;
-        // one load path for both lists, through L2 (a line of the dynamic queue may be stale in L1)
-        const uint4* q = reinterpret_cast<const uint4*>((src == 1 ? p.tasks : p.dyn_tasks) + ti);
-        const uint4 w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2), w3 = __ldcg(q + 3);
+        if (code == kJobQuit) break;
+        Slot* const slot = ctl->slots + (code & 15u);
+        const int tile = (int)((code >> 4) & 0xfffffu);
+        const uint32_t in_link = (code >> 24) & 15u, out_link = code >> 28;
         SwTask task;
-        task.a_base = ((uint64_t)w0.y << 32) | w0.x; task.b_base = ((uint64_t)w0.w << 32) | w0.z;
-        task.c_base = ((uint64_t)w1.y << 32) | w1.x; task.a_len = w1.z; task.b_len = w1.w;
-        task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w; task.best0 = w3.x;
-        if (task.rclass != (uint32_t)R || task.ncols == 0) continue;
+        {
+            const uint4* q = reinterpret_cast<const uint4*>(&slot->task);
+            const uint4 w0 = q[0], w1 = q[1], w2 = q[2];
+            task.a_base = ((uint64_t)w0.y << 32) | w0.x; task.b_base = ((uint64_t)w0.w << 32) | w0.z;
+            task.c_base = ((uint64_t)w1.y << 32) | w1.x; task.a_len = w1.z; task.b_len = w1.w;
+            task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w;
+        }
 
         const int a_len = (int)task.a_len, b_len = (int)task.b_len, ncols = (int)task.ncols;
         const bool a_rev = task.flags & kARev, a_comp = task.flags & kAComp;
         const bool b_rev = task.flags & kBRev, b_comp = task.flags & kBComp;
         const bool c_rev = task.flags & kCRev;
         const int rows = a_len > b_len ? a_len : b_len;
-        const int ntiles = (rows + 32 * R - 1) / (32 * R);
         const int total_steps = (ncols + 31 + kUnroll - 1) & ~(kUnroll - 1);   // the step body is unrolled kUnroll x (pad steps are inert)
         // steps the bias may run before the 16-bit lanes could overflow (>= kChunk by construction of the cap)
         const int hbound = p.match * (rows < ncols ? rows : ncols);       // no alignment of this task can score more
@@ -354,22 +573,21 @@ sw_wavefront_kernel(const SwParams p)
         const uint32_t sat_thr = hbound <= hcap ? 0xffffu : (uint32_t)(hcap - 32 * p.match);
         uint32_t sat = 0;          // bit h: half h came within 32 steps of the cap
 
-        // running best over tiles, per half: {score, col, row}
-        int bs0 = 0, bc0 = 0, br0 = a_len - 1;
-        if (task.best0) { bs0 = (int)task.best0; bc0 = 0x7fffffff; br0 = 0x7fffffff; }   // a cell reaching best0 ties and wins by column
-        int bs1 = 0, bc1 = 0, br1 = b_len - 1;
-        // An unused half (begin pass) holds the floor in every cell: with a running maximum of 0 every cell would sit
-        // within the sampling margin and send the warp down the exact path at every step. Park its maximum out of reach.
-        if (b_len == 0) bs1 = 256;
-
-        for (int tile = 0; tile < ntiles; ++tile) {
+        {
             const int row0 = tile * 32 * R + lane * R;
-            // One boundary buffer per warp, updated in place: tile q reads column c of the row above it at the refill of
-            // the chunk containing c (step <= c) and writes its own last row for column c at the flush after step c+31.
-            uint2* const bnd_in = bnd0;
-            uint2* const bnd_out = bnd0;
-            const bool write_bnd = (tile + 1 < ntiles);
-            const bool stage_lane = write_bnd && lane == 31;
+            // Links: the row above this tile comes in column by column from the warp that runs tile-1 (in_link), this
+            // tile's last row goes out to the warp that runs tile+1 (out_link). Ids below kRings are shared-memory
+            // rings, the others global buffers (updated in place: a later producer of the same buffer is a dependent of
+            // its earlier consumer, and the scheduler hands a buffer out again only when its consumer has finished).
+            const bool has_in = in_link != kNoLink, has_out = out_link != kNoLink;
+            const bool in_ring = in_link < (uint32_t)kRings, out_ring = out_link < (uint32_t)kRings;
+            const uint2* const ring_in = rings + (in_ring ? in_link : 0u) * kRingCols;
+            uint2* const ring_out = rings + (out_ring ? out_link : 0u) * kRingCols;
+            const uint2* const g_in = gbuf0 + (size_t)(has_in && !in_ring ? in_link - kRings : 0u) * p.bnd_stride;
+            uint2* const g_out = gbuf0 + (size_t)(has_out && !out_ring ? out_link - kRings : 0u) * p.bnd_stride;
+            LinkCtl* const lin = ctl->links + (has_in ? in_link : 0u);
+            LinkCtl* const lout = ctl->links + (has_out ? out_link : 0u);
+            const bool stage_lane = has_out && lane == 31;
 
             __syncwarp();
             // ---- profile of this tile: prof[code][group][lane].{x,y,z,w} = (S_A | S_B << 16) + 2*ext of row 4*group+w
@@ -406,8 +624,13 @@ sw_wavefront_kernel(const SwParams p)
             // column's bias, i.e. one ext too strictly, hence open + (stride-1)*ext.
             static_assert(NMSV_SAMPLE_STRIDE >= 2, "the threshold must stay non-negative: sw_bias + 2*ext >= margin");
             const uint32_t MARGIN2 = (uint32_t)((p.open + (NMSV_SAMPLE_STRIDE - 1) * ext) * 65537);
-            // later tiles start their running maximum at (best of the earlier tiles - 1), per half
-            uint32_t bestprev = FLOOR0 + pack16(bs0 > 0 ? bs0 - 1 : 0, bs1 > 0 ? bs1 - 1 : 0);
+            // the running maximum starts at (a score the task is already known to reach) - 1, per half: only cells that
+            // can still win or tie are examined. The bound is shared by the tiles of the task through the slot.
+            uint32_t bestprev;
+            {
+                const int l0 = (int)ld_vol(&slot->lb[0]), l1 = (int)ld_vol(&slot->lb[1]);
+                bestprev = FLOOR0 + pack16(l0 > 0 ? l0 - 1 : 0, l1 > 0 ? l1 - 1 : 0);
+            }
             uint32_t flb = FLOOR0 + p.ext2;     // floor of row k at step t is flb + (t+k)*ext2 = FLOOR0 + (t - tbase + k)*ext2
             uint32_t h_last = FLOOR0 + (uint32_t)(R - 1) * p.ext2, f_out = EF0 + (uint32_t)R * p.ext2, diag = FLOOR0 - p.ext2;
             int tbase = -1;          // bias of row k at step t = (t - tbase + k) * ext ; "after step -1" row 0 carries 0
@@ -527,28 +750,18 @@ sw_wavefront_kernel(const SwParams p)
                     tbase = t0 - 1;
                     flb = FLOOR0 - (uint32_t)tbase * p.ext2;
                 }
-                // ---- refill: columns [t0, t0+kChunk) of the read ring and of the boundary ring
+                // ---- refill: columns [t0, t0+kChunk) of the read ring
                 __syncwarp();
                 const bool prefetched = tma_task && t0 >= kChunk && t0 + kChunk <= ncols;   // issued one chunk ago
+                if (!prefetched) {
 #pragma unroll
-                for (int u = 0; u < kChunk / 32; ++u) {
-                    const int col = t0 + u * 32 + lane;
-                    uint8_t c = (uint8_t)kPadCode;
-                    uint2 bv = make_uint2(FLOOR0, EF0);
-                    if (col < ncols) {
-                        if (!prefetched)
-                            c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
-                        if (tile > 0) bv = __ldcg(bnd_in + col);
-                    }
-                    // lane 0 consumes entry `col` at step col as (H of row -1 for the next step's diagonal, F entering
-                    // row 0): biases (col - 1 - tbase) * ext and (col - tbase) * ext
-                    const uint32_t bb = (uint32_t)((col - tbase) * ext) * 65537u;
-                    bv.x += bb - p.ext2; bv.y += bb;
-                    if (!prefetched) {
+                    for (int u = 0; u < kChunk / 32; ++u) {
+                        const int col = t0 + u * 32 + lane;
+                        uint8_t c = (uint8_t)kPadCode;
+                        if (col < ncols) c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
                         rring[col & (kRing - 1)] = c;
                         rring[(col & (kRing - 1)) + kRing] = c;
                     }
-                    bring[col & (kChunk - 1)] = bv;
                 }
                 if (prefetched) {               // the bulk copies issued one chunk ago have landed?
                     // votes make the outcome warp-uniform in the compiler's eyes
@@ -577,13 +790,34 @@ sw_wavefront_kernel(const SwParams p)
                 const int t1 = (t0 + kChunk < total_steps) ? t0 + kChunk : total_steps;
                 for (int g0 = t0; g0 < t1; g0 += 32) {
                     const int g1 = (g0 + 32 < t1) ? g0 + 32 : t1;     // g1 - g0 is even (total_steps is even)
+                    // ---- boundary inputs of lane 0 for the columns [g0, g0+32): the last row of the tile above, from its
+                    //      link once the producer has flushed them (it has finished the group after this one by then)
+                    {
+                        const int col = g0 + lane;
+                        uint2 bv = make_uint2(FLOOR0, EF0);
+                        if (has_in) {
+                            link_wait(&lin->produced, (uint32_t)(g0 + 32 < ncols ? g0 + 32 : ncols));
+                            if (col < ncols) bv = in_ring ? ring_in[col & (kRingCols - 1)] : __ldcg(g_in + col);
+                        }
+                        // lane 0 consumes entry `col` at step col as (H of row -1 for the next step's diagonal, F entering
+                        // row 0): biases (col - 1 - tbase) * ext and (col - tbase) * ext
+                        const uint32_t bb = (uint32_t)((col - tbase) * ext) * 65537u;
+                        bv.x += bb - p.ext2; bv.y += bb;
+                        __syncwarp();
+                        bring[lane] = bv;
+                        __syncwarp();
+                        if (has_in && in_ring && lane == 0) {
+                            __threadfence_block();
+                            *reinterpret_cast<volatile uint32_t*>(&lin->consumed) = (uint32_t)(g0 + 32);
+                        }
+                    }
                     for (int t = g0; t < g1; t += kUnroll) {        // g0, g1 and total_steps are multiples of kUnroll
                         uint32_t FL[R + kUnroll - 1];      // floors of (step t+u, row k) = FL[u + k]: warp-uniform sliding window
                         FL[0] = flb + (uint32_t)t * p.ext2;
 #pragma unroll
                         for (int i = 1; i < R + kUnroll - 1; ++i)      // IMAD chain, FMA pipe
                             asm("mad.lo.u32 %0, %1, 65537, %2;" : "=r"(FL[i]) : "r"(ext_v), "r"(FL[i - 1]));
-                        const char* bq = bsrc + (uint32_t)(t & (kChunk - 1)) * bstride;
+                        const char* bq = bsrc + (uint32_t)(t & 31) * bstride;
                         const uint8_t* rq = rlane + (t & (kRing - 1));
                         uint2* sq = bstage + (t & 31);
 #pragma unroll
@@ -603,55 +837,62 @@ sw_wavefront_kernel(const SwParams p)
                             const uint32_t o = __shfl_xor_sync(kFull, wb, off);
                             wb = __vimax3_s16x2(wb, o, o);
                         }
-                        const uint32_t lift = wb - 0x00010001u;      // both halves >= bias >= 1: no borrow
-                        bestprev = __vimax3_s16x2(bestprev, lift, lift);
                         // true maxima so far (the running maximum sits at the row-0 bias of step g1-1; no borrow: it is
                         // never below the floor). A parked half (unused B of a begin task) reads 255.
-                        const uint32_t tm = wb - (flb + (uint32_t)(g1 - 1) * p.ext2);
+                        const uint32_t flg = flb + (uint32_t)(g1 - 1) * p.ext2;
+                        const uint32_t tm = wb - flg;
                         sat |= ((tm & 0xffffu) > sat_thr ? 1u : 0u) | ((tm >> 16) > sat_thr ? 2u : 0u);
+                        // the tiles of the task share what they know: a cell of ANY tile is a lower bound of the result
+                        const uint32_t l0 = ld_vol(&slot->lb[0]), l1 = ld_vol(&slot->lb[1]);
+                        if (lane == 0) {
+                            if ((tm & 0xffffu) > l0) atomicMax(&slot->lb[0], tm & 0xffffu);
+                            if ((tm >> 16) > l1) atomicMax(&slot->lb[1], tm >> 16);
+                        }
+                        const uint32_t lbp = (l0 | (l1 << 16)) + flg;        // both < 32768 by the cap: no carry
+                        wb = __vimax3_s16x2(wb, lbp, lbp);
+                        const uint32_t lift = wb - 0x00010001u;      // both halves >= bias >= 1: no borrow
+                        bestprev = __vimax3_s16x2(bestprev, lift, lift);
                     }
                     // ---- flush the staged boundary row of this group: entry q was produced at step g0+q for column
                     //      g0+q-31; remove its bias and store 32 columns with one coalesced 256-byte write
-                    if (write_bnd) {
+                    if (has_out) {
                         __syncwarp();
                         const int tp = g0 + lane;
                         const int col = tp - 31;
+                        // columns [0, cmax) are flushed after this group (the last group ends at step >= ncols + 30)
+                        const int cmax = g1 - 31 < ncols ? (g1 - 31 > 0 ? g1 - 31 : 0) : ncols;
+                        // a ring holds kRingCols columns: do not overwrite what the consumer has not copied yet
+                        if (out_ring) link_wait(&lout->consumed, (uint32_t)(cmax > kRingCols ? cmax - kRingCols : 0));
                         if (tp < g1 && col >= 0 && col < ncols) {
                             uint2 v = bstage[lane];
                             const uint32_t bb = (uint32_t)((tp - tbase + R - 1) * ext) * 65537u;   // row R-1 at step tp
                             v.x -= bb; v.y -= bb + p.ext2;
-                            __stcg(bnd_out + col, v);
+                            if (out_ring) ring_out[col & (kRingCols - 1)] = v;
+                            else __stcg(g_out + col, v);
                         }
+                        if (out_ring) __threadfence_block(); else __threadfence();
                         __syncwarp();
+                        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lout->produced) = (uint32_t)cmax;
                     }
                 }
             }
 
-            // ---- tile epilogue: warp arg-best per half, merge into the running best (later tiles hold larger rows)
+            // ---- tile epilogue: warp arg-best per half, merged into the task's result (lane 0, under the block lock)
             const uint32_t fl = flb + (uint32_t)(total_steps - 1) * p.ext2;     // floor of the last step
             // Every lane resolves its slots, whether it wrote them in this tile or not (a per-lane "valid" flag would
             // cost the compiler its convergence analysis of the loop above): a lane that holds the warp-wide maximum rose
-            // to it in this tile, so its slot is current; any other lane loses the arg-best below whatever it reads.
-            int s = (int)(bestprev & 0xffffu) - (int)(fl & 0xffffu), c = 0, r = 0;
-            resolve_snap(0, c, r);
-            if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
-            warp_argbest(s, c, r);
-            if (s > bs0 || (s == bs0 && s > 0 && c < bc0)) { bs0 = s; bc0 = c; br0 = r; }
-            s = (int)(bestprev >> 16) - (int)(fl >> 16);
-            resolve_snap(1, c, r);
-            if (s <= 0) { s = 0; c = 0x7fffffff; r = 0x7fffffff; }
-            warp_argbest(s, c, r);
-            if (s > bs1 || (s == bs1 && s > 0 && c < bc1)) { bs1 = s; bc1 = c; br1 = r; }
-        }
-
-        if (lane == 0) {
-            SwResult res;
-            res.score[0] = (sat & 1u) ? -1 : bs0; res.row[0] = br0; res.col[0] = bc0;
-            res.score[1] = b_len ? ((sat & 2u) ? -1 : bs1) : 0; res.row[1] = br1; res.col[1] = bc1;
-            const bool is_begin = task.flags & kTaskBegin;
-            (is_begin ? p.rev_results : p.fwd_results)[task.out] = res;
-            if (p.cells) atomicAdd(&p.cells[is_begin ? 1 : 0], (unsigned long long)(a_len + b_len) * (unsigned long long)ncols);
-            if (!is_begin && p.hook) sw_task_done(p.hook, p.group_remaining, task.out);
+            // to it in this tile, so its slot is current; any other lane loses the arg-best below whatever it reads. A
+            // maximum that only came in through the shared bound belongs to another tile, which reports it with its cell.
+            int s0 = (int)(bestprev & 0xffffu) - (int)(fl & 0xffffu), c0 = 0, r0 = 0;
+            resolve_snap(0, c0, r0);
+            if (s0 <= 0) { s0 = 0; c0 = 0x7fffffff; r0 = 0x7fffffff; }
+            warp_argbest(s0, c0, r0);
+            int s1 = (int)(bestprev >> 16) - (int)(fl >> 16), c1 = 0, r1 = 0;
+            resolve_snap(1, c1, r1);
+            if (s1 <= 0) { s1 = 0; c1 = 0x7fffffff; r1 = 0x7fffffff; }
+            warp_argbest(s1, c1, r1);
+            if (lane == 0) finish_job(ctl, p, code, s0, c0, r0, s1, c1, r1, sat);
+            __syncwarp();
         }
     }
 }
