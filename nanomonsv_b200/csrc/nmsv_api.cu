@@ -73,6 +73,8 @@ struct nmsv_ctx {
     int sm_clock_khz = 0;
     int blocks_per_sm[8] = {0};
     void* snap = nullptr;      // per resident warp: column snapshots of the running-maximum tracker (nmsv_sw.cuh)
+    void* rings = nullptr;     // per resident block: kRings boundary rings of ring_cols columns (nmsv_sw.cuh)
+    uint32_t ring_cols = 1024;
     int prune = 1;             // nmsv_set_option("prune"): skip alignments that cannot change any output
     int jump_bps = 0;          // resident blocks per SM of the sw_jump kernel (set once)
     mutable std::string error;
@@ -206,6 +208,13 @@ extern "C" int nmsv_create(nmsv_ctx** out, int device)
         int g = 0;
         for (int c = 0; c < kNumClasses; ++c) g = std::max(g, ctx->prop.multiProcessorCount * std::max(1, ctx->blocks_per_sm[c]));
         CREATE_TRY(cudaMalloc(&ctx->snap, (size_t)g * kWarpsPerBlock * kSnapWords * 32 * sizeof(uint4)));
+        // boundary rings between the tiles of a task: 1024 columns x 8 B x kRings per block = 24 MB for 592 blocks, far
+        // below the L2 size, rewritten every few hundred microseconds (NMSV_RING_COLS: measurement knob, power of two)
+        if (const char* e = getenv("NMSV_RING_COLS")) {
+            const int v = atoi(e);
+            if (v >= 256 && (v & (v - 1)) == 0) ctx->ring_cols = (uint32_t)v;
+        }
+        CREATE_TRY(cudaMalloc(&ctx->rings, (size_t)g * kRings * ctx->ring_cols * sizeof(uint2)));
     }
     {   // keep freed blocks cached in the stream-ordered pool: plans are created and destroyed per batch
         cudaMemPool_t pool;
@@ -224,6 +233,7 @@ extern "C" void nmsv_destroy(nmsv_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
     if (ctx->snap) cudaFree(ctx->snap);
+    if (ctx->rings) cudaFree(ctx->rings);
     delete ctx;
 }
 
@@ -1098,6 +1108,7 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     memset(&sp, 0, sizeof(sp));
     sp.codes = pl->st.codes.as<uint8_t>();
     sp.bnd = pl->bnd.as<uint2>(); sp.bnd_stride = pl->bnd_stride; sp.snap = (uint4*)ctx->snap;
+    sp.rings = (uint2*)ctx->rings; sp.ring_cols = ctx->ring_cols;
     sp.match = pl->sc.match; sp.mismatch = pl->sc.mismatch; sp.open = pl->sc.gap_open; sp.ext = pl->sc.gap_extend;
     fill_packed(sp);
     sp.fwd_results = pl->fwd.as<SwResult>(); sp.rev_results = pl->rev.as<SwResult>();
@@ -1380,6 +1391,7 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     SwParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.codes = st.codes.as<uint8_t>(); sp.bnd = bnd.as<uint2>(); sp.bnd_stride = stride; sp.snap = (uint4*)ctx->snap;
+    sp.rings = (uint2*)ctx->rings; sp.ring_cols = ctx->ring_cols;
     sp.match = sc->match; sp.mismatch = sc->mismatch; sp.open = sc->gap_open; sp.ext = sc->gap_extend;
     fill_packed(sp);
     sp.tasks = tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = n_pairs;

@@ -13,10 +13,11 @@
 //   * the substitution scores come from a per-warp shared-memory profile prof[code][row] (LDS.128, conflict
 //     free) so the inner loop has no compares; the read is staged through a shared-memory ring.
 //   * templates longer than one tile: the tiles of a task are JOBS that the warps of one block claim in order, so the
-//     tiles of a task run side by side on different warps, each lagging its producer by two 32-column groups; the H/F
-//     row between two tiles is handed over through a 128-column shared-memory ring with two progress counters
-//     (no global round trip, no scratch that grows with the read, and the serial chain of a task is one tile, not
-//     all of them). Only tasks with more tiles than a block has warps spill every fourth boundary row to global.
+//     tiles of a task run side by side on different warps, each lagging its producer by a few 32-column groups; the H/F
+//     row between two tiles is handed over through a small ring (1024 columns, 8 B each, L2 resident) with two
+//     progress counters in shared memory: no scratch that grows with the read, no DRAM traffic, and the serial chain
+//     of a task is one tile, not all of them. Only tasks with more tiles than a block has warps keep every fourth
+//     boundary row in a buffer as long as the read.
 //   * every stored value of (step t, strip row k) is  true value + a + (t - tbase + k) * ext  -- an anti-diagonal
 //     bias: a value that moves one column to the right (E) or one row down (F) meets a bias that is ext larger,
 //     so BOTH gap extensions cost no instruction; the zero floor of local alignment becomes a sliding window of
@@ -120,8 +121,10 @@ struct SwParams {
     SwResult* fwd_results;         // results of forward tasks (static or queued by the continuation)
     SwResult* rev_results;         // results of begin-pass tasks (kTaskBegin)
     unsigned long long* cells;     // optional: [0] += forward cells executed, [1] += begin-pass cells executed
-    uint2* bnd;                    // [grid warps][bnd_stride] tile-boundary scratch (H, F of a tile's last row)
+    uint2* bnd;                    // [grid blocks][kGBufs][bnd_stride] whole-read boundary buffers (tasks of > kW tiles only)
     uint32_t bnd_stride;
+    uint2* rings;                  // [grid blocks][kRings][ring_cols] boundary rings between the tiles of a task
+    uint32_t ring_cols;            // power of two
     uint4* snap;                   // [grid warps][kSnapWords * 32] column snapshots of the running-maximum tracker
     int match, mismatch, open, ext;
     uint32_t neg_open2;     // (-open, -open) packed: DPX add operand, read from the constant bank
@@ -139,12 +142,17 @@ struct SwParams {
 // ---- block-level job scheduler (shared memory) ------------------------------------------------------------------------
 // A job = one tile (32*R rows) of one task over all columns. The warps of a block claim jobs in sequence (tile after tile
 // of a task, task after task from the global lists); tile j+1 consumes the last row (H, F per column) of tile j through
-// a link: a shared-memory ring with `produced` / `consumed` column counters, or -- for the link into every kW-th job of a
-// task with more than kW tiles, whose consumer can only be claimed a whole tile later -- one of two global buffers.
+// a link: a ring of ring_cols columns in global memory (it stays in L2: the rings of all blocks together are a few tens
+// of MB that are rewritten every few hundred microseconds) with `produced` / `consumed` column counters in shared
+// memory, or -- for the link into every kW-th job of a task with more than kW tiles, whose consumer can only be claimed
+// a whole tile later -- one of two buffers as long as the read. (Rings in shared memory were measured first: 128
+// columns is all that fits beside the profiles, and with so little slack the warps of a block -- which sit on different
+// schedulers next to warps of other blocks and take the exact path of the running maximum at different times -- spent
+// 9 % of their time waiting for each other.)
 constexpr int kW = kWarpsPerBlock;
 constexpr int kSlots = kW + 2;         // tasks in flight per block (at most kW running jobs + the task being dealt out)
 constexpr int kRings = kW + 1;         // live ring links <= kW - 1 running consumers + the claimed job's in- and out-link
-constexpr int kRingCols = 128;         // columns per ring; a consumer lags its producer by 2..5 groups of 32 columns
+         // columns per ring; a consumer lags its producer by 2..5 groups of 32 columns
 constexpr int kGBufs = 2;              // global boundary buffers per block
 constexpr uint32_t kNoLink = 0xfu;
 constexpr uint32_t kJobQuit = 0xffffffffu, kJobRetry = 0xfffffffeu;
@@ -175,7 +183,7 @@ template <int R>
 __host__ __device__ constexpr size_t warp_smem_bytes()
 {
     return (size_t)kNumCodes * groups_of<R>() * 32 * 16   // profile, uint4 [code][group][lane]
-         + (size_t)32 * 8                                   // boundary inputs of lane 0 for one group of 32 columns, biased
+         + (size_t)kChunk * 8                               // boundary inputs of lane 0 for one chunk of columns, biased
          + (size_t)32 * 8                                   // boundary staging (outputs of lane 31), one group
          + (size_t)16                                       // constant slot read by lanes 1..31 instead of the ring
          + (size_t)16                                       // mbarrier of the TMA (cp.async.bulk) read staging
@@ -185,7 +193,7 @@ __host__ __device__ constexpr size_t warp_smem_bytes()
 template <int R>
 __host__ __device__ constexpr size_t block_smem_bytes()
 {
-    return kCtlBytes + (size_t)kRings * kRingCols * 8 + (size_t)kWarpsPerBlock * warp_smem_bytes<R>();
+    return kCtlBytes + (size_t)kWarpsPerBlock * warp_smem_bytes<R>();
 }
 
 __device__ __forceinline__ uint32_t pack16(int lo, int hi)
@@ -489,11 +497,11 @@ sw_wavefront_kernel(const SwParams p)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     BlockCtl* const ctl = reinterpret_cast<BlockCtl*>(smem_raw);
-    uint2* const rings = reinterpret_cast<uint2*>(smem_raw + kCtlBytes);               // [kRings][kRingCols]
-    uint8_t* wbase = smem_raw + kCtlBytes + (size_t)kRings * kRingCols * 8 + (size_t)warp * warp_smem_bytes<R>();
+    uint2* const rings = p.rings + (size_t)blockIdx.x * kRings * p.ring_cols;          // [kRings][ring_cols]
+    uint8_t* wbase = smem_raw + kCtlBytes + (size_t)warp * warp_smem_bytes<R>();
     uint4* prof = reinterpret_cast<uint4*>(wbase);
     uint2* bring = reinterpret_cast<uint2*>(wbase + (size_t)kNumCodes * G * 32 * 16);
-    uint2* bstage = bring + 32;
+    uint2* bstage = bring + kChunk;
     uint2* bconst = bstage + 32;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bconst + 2);
     uint8_t* rring = reinterpret_cast<uint8_t*>(bconst + 4);
@@ -581,10 +589,12 @@ sw_wavefront_kernel(const SwParams p)
             // its earlier consumer, and the scheduler hands a buffer out again only when its consumer has finished).
             const bool has_in = in_link != kNoLink, has_out = out_link != kNoLink;
             const bool in_ring = in_link < (uint32_t)kRings, out_ring = out_link < (uint32_t)kRings;
-            const uint2* const ring_in = rings + (in_ring ? in_link : 0u) * kRingCols;
-            uint2* const ring_out = rings + (out_ring ? out_link : 0u) * kRingCols;
-            const uint2* const g_in = gbuf0 + (size_t)(has_in && !in_ring ? in_link - kRings : 0u) * p.bnd_stride;
-            uint2* const g_out = gbuf0 + (size_t)(has_out && !out_ring ? out_link - kRings : 0u) * p.bnd_stride;
+            // column c of a link lives at base[c & mask]: a ring wraps, a whole-read buffer does not
+            const uint2* const b_in = in_ring ? rings + (size_t)in_link * p.ring_cols
+                                              : gbuf0 + (size_t)(has_in ? in_link - kRings : 0u) * p.bnd_stride;
+            uint2* const b_out = out_ring ? rings + (size_t)out_link * p.ring_cols
+                                          : gbuf0 + (size_t)(has_out ? out_link - kRings : 0u) * p.bnd_stride;
+            const uint32_t m_in = in_ring ? p.ring_cols - 1u : 0xffffffffu, m_out = out_ring ? p.ring_cols - 1u : 0xffffffffu;
             LinkCtl* const lin = ctl->links + (has_in ? in_link : 0u);
             LinkCtl* const lout = ctl->links + (has_out ? out_link : 0u);
             const bool stage_lane = has_out && lane == 31;
@@ -750,18 +760,34 @@ sw_wavefront_kernel(const SwParams p)
                     tbase = t0 - 1;
                     flb = FLOOR0 - (uint32_t)tbase * p.ext2;
                 }
-                // ---- refill: columns [t0, t0+kChunk) of the read ring
+                // ---- refill: columns [t0, t0+kChunk) of the read ring and of lane 0's boundary inputs (the last row of the
+                //      tile above, from its link once the producer has published them)
                 __syncwarp();
                 const bool prefetched = tma_task && t0 >= kChunk && t0 + kChunk <= ncols;   // issued one chunk ago
-                if (!prefetched) {
+                if (has_in) link_wait(&lin->produced, (uint32_t)(t0 + kChunk < ncols ? t0 + kChunk : ncols));
 #pragma unroll
-                    for (int u = 0; u < kChunk / 32; ++u) {
-                        const int col = t0 + u * 32 + lane;
-                        uint8_t c = (uint8_t)kPadCode;
-                        if (col < ncols) c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
+                for (int u = 0; u < kChunk / 32; ++u) {
+                    const int col = t0 + u * 32 + lane;
+                    uint8_t c = (uint8_t)kPadCode;
+                    uint2 bv = make_uint2(FLOOR0, EF0);
+                    if (col < ncols) {
+                        if (!prefetched)
+                            c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
+                        if (has_in) bv = __ldcg(b_in + ((uint32_t)col & m_in));
+                    }
+                    // lane 0 consumes entry `col` at step col as (H of row -1 for the next step's diagonal, F entering
+                    // row 0): biases (col - 1 - tbase) * ext and (col - tbase) * ext
+                    const uint32_t bb = (uint32_t)((col - tbase) * ext) * 65537u;
+                    bv.x += bb - p.ext2; bv.y += bb;
+                    if (!prefetched) {
                         rring[col & (kRing - 1)] = c;
                         rring[(col & (kRing - 1)) + kRing] = c;
                     }
+                    bring[col & (kChunk - 1)] = bv;
+                }
+                if (has_in && in_ring) {          // the ring entries of this chunk may be overwritten now
+                    __syncwarp();
+                    if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lin->consumed) = (uint32_t)(t0 + kChunk);
                 }
                 if (prefetched) {               // the bulk copies issued one chunk ago have landed?
                     // votes make the outcome warp-uniform in the compiler's eyes
@@ -790,34 +816,13 @@ sw_wavefront_kernel(const SwParams p)
                 const int t1 = (t0 + kChunk < total_steps) ? t0 + kChunk : total_steps;
                 for (int g0 = t0; g0 < t1; g0 += 32) {
                     const int g1 = (g0 + 32 < t1) ? g0 + 32 : t1;     // g1 - g0 is even (total_steps is even)
-                    // ---- boundary inputs of lane 0 for the columns [g0, g0+32): the last row of the tile above, from its
-                    //      link once the producer has flushed them (it has finished the group after this one by then)
-                    {
-                        const int col = g0 + lane;
-                        uint2 bv = make_uint2(FLOOR0, EF0);
-                        if (has_in) {
-                            link_wait(&lin->produced, (uint32_t)(g0 + 32 < ncols ? g0 + 32 : ncols));
-                            if (col < ncols) bv = in_ring ? ring_in[col & (kRingCols - 1)] : __ldcg(g_in + col);
-                        }
-                        // lane 0 consumes entry `col` at step col as (H of row -1 for the next step's diagonal, F entering
-                        // row 0): biases (col - 1 - tbase) * ext and (col - tbase) * ext
-                        const uint32_t bb = (uint32_t)((col - tbase) * ext) * 65537u;
-                        bv.x += bb - p.ext2; bv.y += bb;
-                        __syncwarp();
-                        bring[lane] = bv;
-                        __syncwarp();
-                        if (has_in && in_ring && lane == 0) {
-                            __threadfence_block();
-                            *reinterpret_cast<volatile uint32_t*>(&lin->consumed) = (uint32_t)(g0 + 32);
-                        }
-                    }
                     for (int t = g0; t < g1; t += kUnroll) {        // g0, g1 and total_steps are multiples of kUnroll
                         uint32_t FL[R + kUnroll - 1];      // floors of (step t+u, row k) = FL[u + k]: warp-uniform sliding window
                         FL[0] = flb + (uint32_t)t * p.ext2;
 #pragma unroll
                         for (int i = 1; i < R + kUnroll - 1; ++i)      // IMAD chain, FMA pipe
                             asm("mad.lo.u32 %0, %1, 65537, %2;" : "=r"(FL[i]) : "r"(ext_v), "r"(FL[i - 1]));
-                        const char* bq = bsrc + (uint32_t)(t & 31) * bstride;
+                        const char* bq = bsrc + (uint32_t)(t & (kChunk - 1)) * bstride;
                         const uint8_t* rq = rlane + (t & (kRing - 1));
                         uint2* sq = bstage + (t & 31);
 #pragma unroll
@@ -859,24 +864,31 @@ sw_wavefront_kernel(const SwParams p)
                         __syncwarp();
                         const int tp = g0 + lane;
                         const int col = tp - 31;
-                        // columns [0, cmax) are flushed after this group (the last group ends at step >= ncols + 30)
+                        // Columns [0, cprev) were stored by the previous groups, a whole group ago: the fence has nothing
+                        // to wait for, and the count is published one group late instead of stalling on this group's stores.
+                        const int cprev = g0 - 31 < ncols ? (g0 - 31 > 0 ? g0 - 31 : 0) : ncols;
                         const int cmax = g1 - 31 < ncols ? (g1 - 31 > 0 ? g1 - 31 : 0) : ncols;
-                        // a ring holds kRingCols columns: do not overwrite what the consumer has not copied yet
-                        if (out_ring) link_wait(&lout->consumed, (uint32_t)(cmax > kRingCols ? cmax - kRingCols : 0));
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lout->produced) = (uint32_t)cprev;
+                        // a ring holds ring_cols columns: do not overwrite what the consumer has not copied yet
+                        if (out_ring) link_wait(&lout->consumed, (uint32_t)cmax > p.ring_cols ? (uint32_t)cmax - p.ring_cols : 0u);
                         if (tp < g1 && col >= 0 && col < ncols) {
                             uint2 v = bstage[lane];
                             const uint32_t bb = (uint32_t)((tp - tbase + R - 1) * ext) * 65537u;   // row R-1 at step tp
                             v.x -= bb; v.y -= bb + p.ext2;
-                            if (out_ring) ring_out[col & (kRingCols - 1)] = v;
-                            else __stcg(g_out + col, v);
+                            __stcg(b_out + ((uint32_t)col & m_out), v);
                         }
-                        if (out_ring) __threadfence_block(); else __threadfence();
                         __syncwarp();
-                        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lout->produced) = (uint32_t)cmax;
                     }
                 }
             }
 
+            if (has_out) {          // the last group's stores, then the final count
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lout->produced) = (uint32_t)ncols;
+            }
             // ---- tile epilogue: warp arg-best per half, merged into the task's result (lane 0, under the block lock)
             const uint32_t fl = flb + (uint32_t)(total_steps - 1) * p.ext2;     // floor of the last step
             // Every lane resolves its slots, whether it wrote them in this tile or not (a per-lane "valid" flag would
