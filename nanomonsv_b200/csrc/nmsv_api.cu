@@ -74,6 +74,7 @@ struct nmsv_ctx {
     int blocks_per_sm[8] = {0};
     void* snap = nullptr;      // per resident warp: column snapshots of the running-maximum tracker (nmsv_sw.cuh)
     void* rings = nullptr;     // per resident block: kRings boundary rings of ring_cols columns (nmsv_sw.cuh)
+    void* ring_pos = nullptr;  // per ring: its stream position, carried from launch to launch (entries are lap-tagged)
     uint32_t ring_cols = 1024;
     int prune = 1;             // nmsv_set_option("prune"): skip alignments that cannot change any output
     int jump_bps = 0;          // resident blocks per SM of the sw_jump kernel (set once)
@@ -215,6 +216,10 @@ extern "C" int nmsv_create(nmsv_ctx** out, int device)
             if (v >= 256 && (v & (v - 1)) == 0) ctx->ring_cols = (uint32_t)v;
         }
         CREATE_TRY(cudaMalloc(&ctx->rings, (size_t)g * kRings * ctx->ring_cols * sizeof(uint2)));
+        CREATE_TRY(cudaMalloc(&ctx->ring_pos, (size_t)g * kRings * sizeof(uint32_t)));
+        // lap 0 writes parity 1: zeroed memory reads as "not written yet"
+        CREATE_TRY(cudaMemset(ctx->rings, 0, (size_t)g * kRings * ctx->ring_cols * sizeof(uint2)));
+        CREATE_TRY(cudaMemset(ctx->ring_pos, 0, (size_t)g * kRings * sizeof(uint32_t)));
     }
     {   // keep freed blocks cached in the stream-ordered pool: plans are created and destroyed per batch
         cudaMemPool_t pool;
@@ -234,6 +239,7 @@ extern "C" void nmsv_destroy(nmsv_ctx* ctx)
     if (ctx->own_stream) { cudaStreamSynchronize(ctx->own_stream); cudaStreamDestroy(ctx->own_stream); }
     if (ctx->snap) cudaFree(ctx->snap);
     if (ctx->rings) cudaFree(ctx->rings);
+    if (ctx->ring_pos) cudaFree(ctx->ring_pos);
     delete ctx;
 }
 
@@ -1108,7 +1114,8 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     memset(&sp, 0, sizeof(sp));
     sp.codes = pl->st.codes.as<uint8_t>();
     sp.bnd = pl->bnd.as<uint2>(); sp.bnd_stride = pl->bnd_stride; sp.snap = (uint4*)ctx->snap;
-    sp.rings = (uint2*)ctx->rings; sp.ring_cols = ctx->ring_cols;
+    sp.rings = (uint2*)ctx->rings; sp.ring_cols = ctx->ring_cols; sp.ring_pos = (uint32_t*)ctx->ring_pos;
+    for (sp.ring_shift = 0; (1u << sp.ring_shift) < ctx->ring_cols; ++sp.ring_shift) {}
     sp.match = pl->sc.match; sp.mismatch = pl->sc.mismatch; sp.open = pl->sc.gap_open; sp.ext = pl->sc.gap_extend;
     fill_packed(sp);
     sp.fwd_results = pl->fwd.as<SwResult>(); sp.rev_results = pl->rev.as<SwResult>();
@@ -1391,7 +1398,8 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     SwParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.codes = st.codes.as<uint8_t>(); sp.bnd = bnd.as<uint2>(); sp.bnd_stride = stride; sp.snap = (uint4*)ctx->snap;
-    sp.rings = (uint2*)ctx->rings; sp.ring_cols = ctx->ring_cols;
+    sp.rings = (uint2*)ctx->rings; sp.ring_cols = ctx->ring_cols; sp.ring_pos = (uint32_t*)ctx->ring_pos;
+    for (sp.ring_shift = 0; (1u << sp.ring_shift) < ctx->ring_cols; ++sp.ring_shift) {}
     sp.match = sc->match; sp.mismatch = sc->mismatch; sp.open = sc->gap_open; sp.ext = sc->gap_extend;
     fill_packed(sp);
     sp.tasks = tasks.as<SwTask>(); sp.n_tasks_dev = nullptr; sp.n_tasks = n_pairs;

@@ -124,7 +124,9 @@ struct SwParams {
     uint2* bnd;                    // [grid blocks][kGBufs][bnd_stride] whole-read boundary buffers (tasks of > kW tiles only)
     uint32_t bnd_stride;
     uint2* rings;                  // [grid blocks][kRings][ring_cols] boundary rings between the tiles of a task
+    uint32_t* ring_pos;            // [grid blocks][kRings] stream position of every ring (persists from launch to launch)
     uint32_t ring_cols;            // power of two
+    uint32_t ring_shift;           // log2(ring_cols)
     uint4* snap;                   // [grid warps][kSnapWords * 32] column snapshots of the running-maximum tracker
     int match, mismatch, open, ext;
     uint32_t neg_open2;     // (-open, -open) packed: DPX add operand, read from the constant bank
@@ -143,9 +145,13 @@ struct SwParams {
 // A job = one tile (32*R rows) of one task over all columns. The warps of a block claim jobs in sequence (tile after tile
 // of a task, task after task from the global lists); tile j+1 consumes the last row (H, F per column) of tile j through
 // a link: a ring of ring_cols columns in global memory (it stays in L2: the rings of all blocks together are a few tens
-// of MB that are rewritten every few hundred microseconds) with `produced` / `consumed` column counters in shared
-// memory, or -- for the link into every kW-th job of a task with more than kW tiles, whose consumer can only be claimed
-// a whole tile later -- one of two buffers as long as the read. (Rings in shared memory were measured first: 128
+// of MB that are rewritten every few hundred microseconds), or -- for the link into every kW-th job of a task with more
+// than kW tiles, whose consumer can only be claimed a whole tile later -- one of two buffers as long as the read.
+// A ring is one continuous stream of columns over the life of the context: link after link is appended without gaps,
+// so every entry is written exactly once per lap, and each 8-byte entry carries the parity of its lap in a spare bit
+// (H is never negative). The consumer therefore validates every entry it loads by itself -- no fence and no counter on
+// the producer's side; the only counter is `consumed`, which keeps the producer from lapping the consumer.
+// Whole-read buffers have no lap structure and use a `produced` counter behind a fence instead. (Rings in shared memory were measured first: 128
 // columns is all that fits beside the profiles, and with so little slack the warps of a block -- which sit on different
 // schedulers next to warps of other blocks and take the exact path of the running maximum at different times -- spent
 // 9 % of their time waiting for each other.)
@@ -166,11 +172,14 @@ struct alignas(16) Slot {              // one task in flight in this block (the 
     uint32_t pad_;
 };
 
-struct LinkCtl { uint32_t produced, consumed; };     // columns [0, produced) written / [0, consumed) no longer needed
+// columns [0, produced) written (whole-read buffers only) / [0, consumed) no longer needed; base = position of the
+// link's column 0 in the ring's stream
+struct LinkCtl { uint32_t produced, consumed, base, pad_; };
 
 struct BlockCtl {
     uint32_t lock, quit, n_waiting, cur;             // cur = slot whose tiles are being dealt out (kSlots = none)
     uint32_t slot_busy, ring_busy, gbuf_busy, seq;   // seq = sequence number of the next job
+    uint32_t stream[kRings + kGBufs];                // per ring: stream position where its next link starts
     LinkCtl links[kRings + kGBufs];
     Slot slots[kSlots];
 };
@@ -306,6 +315,22 @@ __device__ __forceinline__ void link_wait(const uint32_t* flag, uint32_t need)
     __threadfence_block();
 }
 
+// some ring entry of the warp is not yet written in this lap: poll (out of line, like every data-dependent loop, and
+// called by the whole warp so that the call site stays convergent; lanes with stale = false return at once)
+__device__ __noinline__ uint2 ring_poll(const uint2* ptr, uint32_t tag, uint2 v, bool stale)
+{
+    const unsigned long long t0 = global_ns();
+    while (__any_sync(kFull, stale)) {        // warp-uniform exit
+        __nanosleep(100);
+        if (stale) {
+            v = __ldcg(ptr);
+            stale = ((v.x >> 15) & 1u) != tag;
+        }
+        if (global_ns() - t0 > kWatchdogNs) __trap();
+    }
+    return v;
+}
+
 __device__ __forceinline__ void ctl_lock(BlockCtl* c)
 {
     const unsigned long long t0 = global_ns();
@@ -418,7 +443,11 @@ __device__ __noinline__ uint32_t claim_job(BlockCtl* ctl, const SwParams& p, uin
                 }
                 if (ok) {
                     ret = ctl->cur | (j << 4) | (s.last_out << 24) | (out << 28);
-                    if (out != kNoLink) { ctl->links[out].produced = 0u; ctl->links[out].consumed = 0u; }
+                    if (out != kNoLink) {
+                        ctl->links[out].produced = 0u; ctl->links[out].consumed = 0u;
+                        ctl->links[out].base = ctl->stream[out];
+                        ctl->stream[out] += s.task.ncols;
+                    }
                     s.last_out = out;
                     s.next_tile = j + 1u;
                     ctl->seq += 1u;
@@ -544,6 +573,7 @@ sw_wavefront_kernel(const SwParams p)
     if (threadIdx.x == 0) {
         ctl->lock = 0; ctl->quit = 0; ctl->n_waiting = 0; ctl->cur = (uint32_t)kSlots;
         ctl->slot_busy = ~((1u << kSlots) - 1u); ctl->ring_busy = ~((1u << kRings) - 1u); ctl->gbuf_busy = 0; ctl->seq = 0;
+        for (int r = 0; r < kRings + kGBufs; ++r) ctl->stream[r] = r < kRings ? p.ring_pos[blockIdx.x * kRings + r] : 0u;
     }
     __syncthreads();               // the only block-wide barrier: from here on the warps meet through the links only
     uint32_t tma_parity = 0;       // phase of the next mbarrier completion to wait for
@@ -597,6 +627,7 @@ sw_wavefront_kernel(const SwParams p)
             const uint32_t m_in = in_ring ? p.ring_cols - 1u : 0xffffffffu, m_out = out_ring ? p.ring_cols - 1u : 0xffffffffu;
             LinkCtl* const lin = ctl->links + (has_in ? in_link : 0u);
             LinkCtl* const lout = ctl->links + (has_out ? out_link : 0u);
+            const uint32_t q_in = in_ring ? lin->base : 0u, q_out = out_ring ? lout->base : 0u;     // stream positions of column 0
             const bool stage_lane = has_out && lane == 31;
 
             __syncwarp();
@@ -764,7 +795,7 @@ sw_wavefront_kernel(const SwParams p)
                 //      tile above, from its link once the producer has published them)
                 __syncwarp();
                 const bool prefetched = tma_task && t0 >= kChunk && t0 + kChunk <= ncols;   // issued one chunk ago
-                if (has_in) link_wait(&lin->produced, (uint32_t)(t0 + kChunk < ncols ? t0 + kChunk : ncols));
+                if (has_in && !in_ring) link_wait(&lin->produced, (uint32_t)(t0 + kChunk < ncols ? t0 + kChunk : ncols));
 #pragma unroll
                 for (int u = 0; u < kChunk / 32; ++u) {
                     const int col = t0 + u * 32 + lane;
@@ -773,7 +804,19 @@ sw_wavefront_kernel(const SwParams p)
                     if (col < ncols) {
                         if (!prefetched)
                             c = p.codes[c_rev ? task.c_base - (uint64_t)col : task.c_base + (uint64_t)col];
-                        if (has_in) bv = __ldcg(b_in + ((uint32_t)col & m_in));
+                    }
+                    if (has_in) {
+                        // a ring entry is valid once it carries the parity of the lap this column belongs to
+                        const uint32_t q = q_in + (uint32_t)col;
+                        const uint2* const ptr = b_in + (q & m_in);
+                        const uint32_t tag = ((q >> p.ring_shift) + 1u) & 1u;
+                        bool stale = false;
+                        if (col < ncols) {
+                            bv = __ldcg(ptr);
+                            stale = in_ring && ((bv.x >> 15) & 1u) != tag;
+                        }
+                        if (__any_sync(kFull, stale)) bv = ring_poll(ptr, tag, bv, stale);
+                        if (in_ring) bv.x &= 0xffff7fffu;
                     }
                     // lane 0 consumes entry `col` at step col as (H of row -1 for the next step's diagonal, F entering
                     // row 0): biases (col - 1 - tbase) * ext and (col - tbase) * ext
@@ -868,23 +911,28 @@ sw_wavefront_kernel(const SwParams p)
                         // to wait for, and the count is published one group late instead of stalling on this group's stores.
                         const int cprev = g0 - 31 < ncols ? (g0 - 31 > 0 ? g0 - 31 : 0) : ncols;
                         const int cmax = g1 - 31 < ncols ? (g1 - 31 > 0 ? g1 - 31 : 0) : ncols;
-                        __threadfence();
-                        __syncwarp();
-                        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lout->produced) = (uint32_t)cprev;
-                        // a ring holds ring_cols columns: do not overwrite what the consumer has not copied yet
-                        if (out_ring) link_wait(&lout->consumed, (uint32_t)cmax > p.ring_cols ? (uint32_t)cmax - p.ring_cols : 0u);
+                        if (out_ring) {
+                            // a ring holds ring_cols columns: do not overwrite what the consumer has not copied yet
+                            link_wait(&lout->consumed, (uint32_t)cmax > p.ring_cols ? (uint32_t)cmax - p.ring_cols : 0u);
+                        } else {
+                            __threadfence();
+                            __syncwarp();
+                            if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lout->produced) = (uint32_t)cprev;
+                        }
                         if (tp < g1 && col >= 0 && col < ncols) {
                             uint2 v = bstage[lane];
                             const uint32_t bb = (uint32_t)((tp - tbase + R - 1) * ext) * 65537u;   // row R-1 at step tp
                             v.x -= bb; v.y -= bb + p.ext2;
-                            __stcg(b_out + ((uint32_t)col & m_out), v);
+                            const uint32_t q = q_out + (uint32_t)col;
+                            if (out_ring) v.x = (v.x & 0xffff7fffu) | ((((q >> p.ring_shift) + 1u) & 1u) << 15);   // lap parity
+                            __stcg(b_out + (q & m_out), v);
                         }
                         __syncwarp();
                     }
                 }
             }
 
-            if (has_out) {          // the last group's stores, then the final count
+            if (has_out && !out_ring) {          // the last group's stores, then the final count
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lout->produced) = (uint32_t)ncols;
@@ -907,6 +955,8 @@ sw_wavefront_kernel(const SwParams p)
             __syncwarp();
         }
     }
+    __syncthreads();          // every warp of the block has left the job loop
+    if (threadIdx.x < kRings) p.ring_pos[blockIdx.x * kRings + threadIdx.x] = ctl->stream[threadIdx.x];
 }
 
 }  // namespace nmsv

@@ -13,7 +13,7 @@ lib=sys.argv[1]; fn=sys.argv[2] if len(sys.argv)>2 else '_ZN4nmsv19sw_wavefront_
 out=subprocess.run(['cuobjdump','-sass','-fun',fn,lib],capture_output=True,text=True).stdout
 ops=[]
 for l in out.splitlines():
-    m=re.match(r"\s+/\*([0-9a-f]{4})\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)(.*?);",l)
+    m=re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(@!?U?P\d+\s+)?([A-Z0-9_.]+)(.*?);",l)
     if m: ops.append((int(m.group(1),16),m.group(3),m.group(4).strip(),m.group(2) or ''))
 best=None
 for i,(a,o,r,pr) in enumerate(ops):
@@ -24,7 +24,9 @@ for i,(a,o,r,pr) in enumerate(ops):
             if t<a:
                 body=[x for x in ops if t<=x[0]<=a]
                 n=sum(1 for x in body if x[1].startswith('VIADDMNMX'))
-                if best is None or n>best[0] or (n==best[0] and len(body)<len(best[3])): best=(n,t,a,body)
+                # the innermost loop that holds the unrolled step body (8 steps x 66 DPX = 528 VIADDMNMX/VIMNMX3 of which
+                # 400 are VIADDMNMX): the smallest body among the loops with at least 300 of them
+                if n>=300 and (best is None or len(body)<len(best[3])): best=(n,t,a,body)
 n,t,a,body=best
 # remove forward-skipped regions: @!P BRA target forward inside loop => exact path skipped
 fast=[];skip_until=None
