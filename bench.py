@@ -4,19 +4,27 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # host-CPU "parasail-equivalent" port
 
-Workload = BASELINE.json configs[1] ("synthetic COLO829-shaped": canonical SV candidates, 30x tumor + 30x control
-ONT-like reads ~10 kb at ~8 % error, +-1 kb templates -> m = 2000). One STEP validates one batch of
---svs-per-gpu candidates (tumor AND control reads) per GPU; the 20k-candidate job of the config is that step
-repeated, so GCUPS and candidates/s do not depend on the batch count. Weak scaling: every rank gets its own
-batch (own seed), no data-path collective; for N > 1 the per-SV counts are merged with one NCCL all-reduce per step.
+Headline workload = BASELINE.json configs[1] ("synthetic COLO829-shaped": canonical SV candidates, 30x tumor + 30x control
+ONT-like reads ~10 kb at ~8 % error, +-1 kb templates -> m = 2000). One STEP validates one batch of --svs-per-gpu
+candidates (tumor AND control reads) per GPU; the 20k-candidate job of the config is that step repeated, so GCUPS and
+candidates/s do not depend on the batch count. Weak scaling: every rank gets its own batch (own seed, same planned work),
+no data-path collective; for N > 1 the per-SV counts are merged with one NCCL all-reduce at the end of the job.
 
 value  = reference-equivalent forward DP cells (sum 2*m*n over every alignment parasail would run) / device time,
          inputs resident in HBM, CUDA events on the launching stream, max over ranks.
-e2e    = the same cells / wall time of nmsv_validate_batch called with pinned HOST buffers (H2D, planning,
-         kernels, D2H inside the timed region), two calls in flight (two contexts, two host threads) so that the
-         upload of one step overlaps the kernels of the previous one; `e2e.serial` is the same with one call at a time.
-Identical templates of one SV (var1 == var2 when there is no insertion) are aligned once on the GPU; the cells
-actually executed are reported as `cells_executed` and are what the roofline fraction is computed from.
+e2e    = the same cells / wall time of nmsv_validate_batch called with pinned HOST buffers (H2D, planning, kernels, D2H
+         inside the timed region), two calls in flight (two contexts, two host threads) so that the upload of one step
+         overlaps the kernels of the previous one; `e2e.serial` is the same with one call at a time.
+The device does not compute every cell the reference computes: identical templates of one SV (var1 == var2 without an
+insertion) are aligned once, reads whose mapping-quality test already fails are only counted, and reference-allele
+alignments are run only for reads that pass the variant tests -- the outputs are identical (`parity_sampled`, tests/).
+`cells_executed` (counted on the device) is what the roofline fraction and `gcups_executed` use; `cells_pruned` says how
+much was skipped.
+
+The same line carries, under `configs`, one entry per BASELINE.json config (1, 3, 4 as single-GPU shape measurements at
+N = 1; 5 = the 10^6-pair kernel sweep, sharded over the N ranks) and, under `parity_sampled`, a comparison of the CUDA
+results with the CPU oracle on a sample of every config (the run aborts non-zero on a mismatch); for N > 1 also a
+`strong` section: ONE fixed job partitioned over the ranks with the product's own sharding (nanomonsv_b200/shard.py).
 """
 from __future__ import annotations
 
@@ -39,10 +47,10 @@ sys.path.insert(0, ROOT)
 # the sampled running maximum = 66 instructions per 32 cells (SASS count)
 DPX_PER_CELL = 66.0 / 32.0
 WORKLOAD = "colo829_shaped"
-# mean EXECUTED forward cells of one synthetic candidate (tumor + control reads, both strands, m = 2000, identical
-# templates counted once), measured on the generator; the per-GPU batch is cut at --svs-per-gpu times this budget so
-# that every rank does equal device work
-CELLS_PER_CANDIDATE = 7.926e9
+# mean statically PLANNED forward cells of one synthetic candidate of the headline workload (tumor + control reads that
+# pass the mapq test, both strands, identical variant templates counted once; the lazily queued reference-allele
+# alignments come on top). The per-GPU batch is cut at --svs-per-gpu times this budget: equal device work per rank.
+CELLS_PER_CANDIDATE = 2.53e9
 
 
 def log(*a):
@@ -60,87 +68,173 @@ def emit(line: dict) -> None:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# workload
+# workloads
 # ----------------------------------------------------------------------------------------------------------------
-def build_batch(n_sv: int, rank: int, args):
-    """One step's batch for one GPU: tumor reads then control reads of the same n_sv candidates."""
+def _mapq_ok(rd, is_sbnd: bool, min_mapq: int) -> bool:
+    if rd.mapq1 is None or rd.mapq1 < min_mapq:
+        return False
+    return is_sbnd or (rd.mapq2 is not None and rd.mapq2 >= min_mapq)
+
+
+def build_batch(n_sv: int, rank: int, args=None, preset: str = WORKLOAD, budget: float | None = -1.0, **over):
+    """One step's batch for one GPU: tumor reads then control reads of the same candidates (canonical or single
+    breakend). budget = planned cells to cut the batch at (-1: CELLS_PER_CANDIDATE * n_sv for the headline workload,
+    None: keep all n_sv candidates)."""
     from nanomonsv_b200 import synth
     from nanomonsv_b200.batch import BatchBuilder
-    from nanomonsv_b200.count_sread_by_alignment import canonical_templates
-    cfg = dataclasses.replace(synth.PRESETS[WORKLOAD], seed=synth.PRESETS[WORKLOAD].seed + 7919 * rank,
-                              contig_len=4_000_000, n_contigs=4)
+    from nanomonsv_b200.count_sread_by_alignment import canonical_templates, sbnd_templates
+    base = synth.PRESETS[preset]
+    kw = dict(seed=base.seed + 7919 * rank, contig_len=4_000_000, n_contigs=4)
+    kw.update(over)
+    cfg = dataclasses.replace(base, **kw)
     t0 = time.time()
-    # weak scaling needs equal work per rank: draw some spare candidates and keep the first ones (in generation
-    # order) whose reference-equivalent cell count reaches the per-GPU budget of n_sv average candidates
-    spare = max(8, n_sv // 5)
+    if budget is not None and budget < 0:
+        budget = CELLS_PER_CANDIDATE * n_sv
+    spare = max(8, n_sv // 5) if budget is not None else 0
     wl = synth.make_workload(cfg, n_sv + spare)
     L = cfg.validate_sequence_length
-    per_sv = []
+    tmpl = {}
     for i, sv in enumerate(wl.svs):
-        bases = sum(len(r.codes) for smp in ("tumor", "control") for r in wl.samples[smp][i])
-        v1, v2, r1, r2, short = canonical_templates(sv.key, wl.fasta, L)
-        distinct = {v1, v2} | ({r1, r2} if short else set())     # identical templates are aligned once on the GPU
-        per_sv.append(2 * sum(len(t) for t in distinct) * bases)
-    budget = CELLS_PER_CANDIDATE * n_sv
-    keep, acc = [], 0
-    for i, c in enumerate(per_sv):
-        if acc >= budget:
-            break
-        keep.append(i); acc += c
+        if sv.is_sbnd:
+            v1, r1 = sbnd_templates(sv.key, wl.fasta, L)
+            tmpl[i] = ([v1, None, r1, None], True, False)
+        else:
+            v1, v2, r1, r2, short = canonical_templates(sv.key, wl.fasta, L)
+            tmpl[i] = ([v1, v2, r1 if short else None, r2 if short else None], False, short)
+    keep = list(range(len(wl.svs)))
+    if budget is not None:
+        # weak scaling needs equal work per rank: keep the first candidates (in generation order) whose planned cell
+        # count reaches the per-GPU budget
+        keep, acc = [], 0.0
+        for i in range(len(wl.svs)):
+            if acc >= budget:
+                break
+            t, is_sbnd, _ = tmpl[i]
+            rows = sum(len(x) for x in {t[0], t[1]} if x)
+            bases = sum(len(r.codes) for smp in ("tumor", "control") for r in wl.samples[smp][i] if _mapq_ok(r, is_sbnd, 0))
+            keep.append(i); acc += 2.0 * rows * bases
     keep_set = set(keep)
     bb = BatchBuilder(score_ratio_thres=1.2, var_read_min_mapq=0)
     for sample in ("tumor", "control"):
         for i in [j for j in wl.sv_order() if j in keep_set]:
-            var1, var2, ref1, ref2, short = canonical_templates(wl.svs[i].key, wl.fasta, L)
-            bb.add_sv([var1, var2, ref1 if short else None, ref2 if short else None], False, short)
+            t, is_sbnd, short = tmpl[i]
+            bb.add_sv(t, is_sbnd, short)
             for rd in wl.samples[sample][i]:
-                bb.add_read(rd.codes, rd.mapq1, rd.mapq2)
+                bb.add_read(rd.codes, rd.mapq1, None if is_sbnd else rd.mapq2)
     pack, svs, reads = bb.finalize()
-    log(f"[rank {rank}] synthetic batch: {len(keep)} candidates x (tumor, control), {len(reads)} reads, "
+    log(f"[rank {rank}] {preset}: {len(keep)} candidates x (tumor, control), {len(reads)} reads, "
         f"{pack.finalize()[0].size / 1e6:.0f} MB of bases, built in {time.time() - t0:.1f}s")
     return cfg, pack, svs, reads
 
 
-def cpu_sample(pack, svs, reads, target_cells: float):
-    """A bounded sample of the batch for the CPU leg: the first SVs (tumor part) until target_cells forward cells.
-    Every alignment the reference would run is listed: each present template and its reverse complement against
-    every read of the SV (no sharing of identical templates, like the reference)."""
-    from nanomonsv_b200 import _lib
-    from nanomonsv_b200.engine import SeqPack
-    codes, offsets, lens = pack.finalize()
-    comp = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
-    sp = SeqPack()
-    t_idx, r_idx = [], []
-    cells = 0
-    n_used = 0
-    for i, sv in enumerate(svs):
-        if cells >= target_cells:
-            break
-        rd_idx = {}
-        for r in range(int(sv["read_begin"]), int(sv["read_end"])):
-            s = int(reads["seq"][r])
-            rd_idx[r] = sp.add_codes(codes[int(offsets[s]):int(offsets[s]) + int(lens[s])])
-        for slot in range(4):
-            t = int(sv["tmpl"][slot])
-            if t == _lib.NMSV_NONE:
-                continue
-            tc = codes[int(offsets[t]):int(offsets[t]) + int(lens[t])]
-            f = sp.add_codes(tc)
-            rc = sp.add_codes(comp[tc[::-1]])
-            for r, ri in rd_idx.items():
-                t_idx += [f, rc]
-                r_idx += [ri, ri]
-                cells += 2 * int(lens[t]) * int(lens[int(reads["seq"][r])])
-        n_used += 1
-    return sp, np.asarray(t_idx, dtype=np.uint32), np.asarray(r_idx, dtype=np.uint32), cells, n_used
+# ----------------------------------------------------------------------------------------------------------------
+# CPU leg: the oracle on a bounded sample (timed = cpu_baseline / reference arm; results = parity check)
+# ----------------------------------------------------------------------------------------------------------------
+_COMP = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
 
 
-def run_cpu(sp, t_idx, r_idx, threads: int):
-    from oracle import oracle as O
-    codes, offsets, lens = sp.finalize()
-    t0 = time.perf_counter()
-    _, used = O.ssw_batch(codes, offsets, lens, t_idx, r_idx, engine="striped", threads=threads)
-    return time.perf_counter() - t0, used
+class OracleJob:
+    """Every alignment the reference would run for the first SVs of a packed batch: each present template and its
+    reverse complement against every read of the SV (no sharing of identical templates, like the reference)."""
+
+    def __init__(self, pack, svs, reads, target_cells: float):
+        from nanomonsv_b200 import _lib
+        codes, offsets, lens = pack.finalize()
+        extra, rc_of = [], {}
+        pos = int(codes.size)
+        off_l, len_l = [], []
+        t_idx, r_idx, rows, slots = [], [], [], []
+        cells = 0
+        n_used = 0
+        for i, sv in enumerate(svs):
+            if cells >= target_cells:
+                break
+            sbnd = bool(sv["flags"] & _lib.SV_SBND)
+            rb, re_ = int(sv["read_begin"]), int(sv["read_end"])
+            seqs = reads["seq"][rb:re_].astype(np.int64)
+            for slot in range(4):
+                t = int(sv["tmpl"][slot])
+                if t == _lib.NMSV_NONE or (sbnd and slot in (1, 3)):
+                    continue
+                rc = int(sv["tmpl_rc"][slot])
+                if rc == _lib.NMSV_NONE:
+                    rc = rc_of.get(t)
+                    if rc is None:
+                        tc = codes[int(offsets[t]):int(offsets[t]) + int(lens[t])]
+                        rc = len(lens) + len(off_l)
+                        rc_of[t] = rc
+                        extra.append(_COMP[tc[::-1]]); off_l.append(pos); len_l.append(len(tc)); pos += len(tc)
+                n = len(seqs)
+                t_idx.append(np.stack([np.full(n, t), np.full(n, rc)], axis=1).ravel())
+                r_idx.append(np.repeat(seqs, 2))
+                rows.append(np.arange(rb, re_)); slots.append(np.full(n, slot))
+                cells += 2 * int(lens[t]) * int(lens[seqs].sum())
+            n_used += 1
+        self.n_svs, self.n_reads = n_used, int(svs["read_end"][n_used - 1]) if n_used else 0
+        self.cells = cells
+        self.codes = np.concatenate([codes] + extra) if extra else codes
+        self.offsets = np.concatenate([offsets, np.asarray(off_l, dtype=np.uint64)])
+        self.lens = np.concatenate([lens, np.asarray(len_l, dtype=np.uint32)])
+        cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dtype=dt)   # noqa: E731
+        self.t_idx, self.r_idx = cat(t_idx, np.uint32), cat(r_idx, np.uint32)
+        self.rows, self.slots = cat(rows, np.int64), cat(slots, np.int64)
+        self.m = self.lens[self.t_idx[0::2]].astype(np.int64) if len(self.t_idx) else np.zeros(0, dtype=np.int64)
+
+    def run(self, threads: int):
+        """(seconds, threads used, results) of the striped AVX2 port with the reversed begin pass for every alignment."""
+        from oracle import oracle as O
+        t0 = time.perf_counter()
+        res, used = O.ssw_batch(self.codes, self.offsets, self.lens, self.t_idx, self.r_idx, engine="striped", threads=threads)
+        return time.perf_counter() - t0, used, res
+
+    def expected(self, res):
+        """ssw_check's 6-tuple per (read, slot) from the oracle's two strands (count_sread_by_alignment.py:151-160)."""
+        f, r = res[0::2], res[1::2]
+        plus = f["score1"] > r["score1"]                       # ties -> '-'
+        m = self.m
+        out = np.zeros(len(f), dtype=[("score", "<i4"), ("qstart", "<i4"), ("qend", "<i4"), ("tstart", "<i4"),
+                                      ("tend", "<i4"), ("strand", "<i4")])
+        out["score"] = np.where(plus, f["score1"], r["score1"])
+        out["qstart"] = np.where(plus, f["read_begin1"] + 1, m - r["read_end1"])
+        out["qend"] = np.where(plus, f["read_end1"] + 1, m - r["read_begin1"])
+        out["tstart"] = np.where(plus, f["ref_begin1"] + 1, r["ref_begin1"] + 1)
+        out["tend"] = np.where(plus, f["ref_end1"] + 1, r["ref_end1"] + 1)
+        out["strand"] = np.where(plus, 1, -1)
+        return out
+
+
+def parity_validate(eng, pack, svs, reads, job: OracleJob, res, full_counts=None) -> dict:
+    """CUDA path vs the oracle on the sampled SVs: a plan that computes EVERY alignment (prune off) must reproduce score,
+    strand and end cell of every (read, template) and the whole 6-tuple wherever the begin pass ran; the default
+    (pruning) plan must give the same counts and records. Returns {checked, equal}; raises on a mismatch."""
+    n_sv, n_rd = job.n_svs, job.n_reads
+    exp = job.expected(res)
+    plan = eng.plan(pack, svs[:n_sv], reads[:n_rd], prune=False)
+    plan.run()
+    c_full, s_full, r_full = plan.download()
+    alns, flags = plan.download_alns()
+    plan.close()
+    got = alns[job.rows, job.slots]
+    cand = (flags[job.rows] & 1) != 0
+    plus = exp["strand"] > 0
+    ok = (got["score"] == exp["score"]) & (got["strand"] == exp["strand"]) & (got["tend"] == exp["tend"])
+    ok &= np.where(plus, got["qend"] == exp["qend"], got["qstart"] == exp["qstart"])          # end cell
+    full = (got["qstart"] == exp["qstart"]) & (got["qend"] == exp["qend"]) & (got["tstart"] == exp["tstart"])
+    ok &= np.where(cand & (exp["score"] > 0), full, True)
+    checked, equal = int(len(exp)), int(ok.sum())
+    plan = eng.plan(pack, svs[:n_sv], reads[:n_rd])
+    plan.run()
+    c_p, s_p, r_p = plan.download()
+    plan.close()
+    same = bool((c_p == c_full).all() and (s_p == s_full).all() and (r_p == r_full).all())
+    if full_counts is not None:      # the sampled SVs inside the full batch
+        same = same and bool((full_counts[:n_sv] == s_p).all())
+    out = {"checked": checked, "equal": equal, "begin_pass_tuples": int((cand & (exp["score"] > 0)).sum()),
+           "sv_candidates": n_sv, "supporting_reads": int(s_full.sum()), "pruned_plan_identical": same}
+    if equal != checked or not same:
+        bad = np.flatnonzero(~ok)[:5]
+        raise SystemExit(f"PARITY MISMATCH against the oracle: {out}; first rows {[(int(job.rows[b]), int(job.slots[b])) for b in bad]}")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -192,29 +286,148 @@ def reference_arm(args, rank: int):
     cfg, pack, svs, reads = build_batch(min(args.svs_per_gpu, 16), 0, args)
     threads = os.cpu_count() or 1
     # calibrate on a small sample, then size one step to ~args.cpu_seconds
-    sp, t, r, cells, _ = cpu_sample(pack, svs, reads, 2e10)
-    dt, used = run_cpu(sp, t, r, threads)
-    target = max(2e10, cells / dt * args.cpu_seconds)
-    sp, t, r, cells, n_used = cpu_sample(pack, svs, reads, target)
+    job = OracleJob(pack, svs, reads, 2e10)
+    dt, used, _ = job.run(threads)
+    job = OracleJob(pack, svs, reads, max(2e10, job.cells / dt * args.cpu_seconds))
     for _ in range(args.warmup):
-        run_cpu(sp, t, r, threads)
+        job.run(threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, used = run_cpu(sp, t, r, threads)
+        _, used, _ = job.run(threads)
     dt = (time.perf_counter() - t0) / args.steps
-    gcups = cells / dt / 1e9
-    sample = (f"{n_used} of the batch's SV candidates (tumor reads), {len(t)} alignments incl. reverse-complement strand "
-              f"and reversed begin pass, {cells / 1e9:.1f} G forward cells per step")
+    gcups = job.cells / dt / 1e9
+    sample = (f"{job.n_svs} of the batch's SV candidates (tumor reads), {len(job.t_idx)} alignments incl. reverse-complement "
+              f"strand and reversed begin pass, {job.cells / 1e9:.1f} G forward cells per step")
     line = {"impl": "reference", "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8->int16 striped SIMD (AVX2)", "data": "synthetic",
             "config": {"workload": f"{WORKLOAD}: m=2000 templates, ~10 kb reads, 8% error; bounded sample per step",
                        "engine": "oracle/nmsv_striped.c (parasail-equivalent port; parasail itself is not installable here)"},
-            "sv_per_s": n_used / 2 / dt,
+            "sv_per_s": job.n_svs / 2 / dt,
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# secondary configs (BASELINE.json configs 1, 3, 4: shapes; 5: the pair sweep)
+# ----------------------------------------------------------------------------------------------------------------
+SHAPES = [
+    # (BASELINE config number, preset, candidates, overrides)
+    (1, "testdata_shaped", 400, dict(contig_len=2_000_000, n_contigs=2)),
+    (3, "insertion_heavy", 120, dict(contig_len=2_000_000, n_contigs=2)),
+    (4, "single_breakend", 2000, dict(contig_len=2_000_000, n_contigs=2)),
+]
+
+
+def time_runs(torch, stream, fn, warmup: int, steps: int) -> float:
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def shape_entry(torch, stream, eng, dpx_peak, number, preset, n_sv, over, cpu_gcups, cpu_seconds, threads):
+    cfg, pack, svs, reads = build_batch(n_sv, 0, None, preset=preset, budget=None, **over)
+    plan = eng.plan(pack, svs, reads)
+    plan.set_profiling(True)
+    ms = time_runs(torch, stream, plan.run, 2, 3)
+    kt = plan.kernel_times()
+    _, supporting, _ = plan.download()
+    st = plan.stats()
+    plan.close()
+    fwd = [(r, t) for name, r, t in kt if name == "sw_forward"]
+    fwd_ms = sum(t for _, t in fwd)
+    entry = {"baseline_config": number, "workload": preset, "sv_candidates": len(svs) // 2, "reads": int(len(reads)),
+             "template_rows": 2 * cfg.validate_sequence_length, "ms": ms, "sv_per_s": (len(svs) // 2) / (ms * 1e-3),
+             "gcups": st["cells_reference"] / ms / 1e6, "gcups_executed": st["cells_executed"] / ms / 1e6,
+             "cells_reference": st["cells_reference"], "cells_executed": st["cells_executed"],
+             "cells_pruned": st["cells_pruned"], "supporting_reads": int(supporting.sum()),
+             "roofline": {"frac": st["cells_executed"] * DPX_PER_CELL / (fwd_ms * 1e-3) / dpx_peak,
+                          "kernels": [f"sw_wavefront_kernel<{r}>" for r, _ in fwd], "kernel_ms": fwd_ms,
+                          "note": "all forward launches of the step together, DPX cost of the R=16 instantiation"}}
+    job = OracleJob(pack, svs, reads, cpu_gcups * 1e9 * cpu_seconds)
+    _, _, res = job.run(threads)
+    entry["parity_sampled"] = parity_validate(eng, pack, svs, reads, job, res, supporting)
+    log(f"[config {number}] {preset}: {entry['gcups_executed']:.0f} GCUPS executed, {entry['sv_per_s']:.0f} SV/s, parity "
+        f"{entry['parity_sampled']['equal']}/{entry['parity_sampled']['checked']}")
+    return entry
+
+
+def pair_sweep_entry(torch, dist, dev, eng, rank, world, total_pairs, cpu_gcups, cpu_seconds, threads):
+    """BASELINE config 5: 10^6 (read, template) pairs, m = 400, read length uniform in 1-50 kb, drawn from a pool of
+    reads, streamed through nmsv_ssw_check_batch (both strands, begin pass, host buffers) in batches; the pairs are
+    dealt to the ranks, no collective on the data path."""
+    from nanomonsv_b200 import SeqPack, synth
+    from oracle import oracle as O
+    t0 = time.time()
+    seqs, t_idx, r_idx = synth.make_pair_sweep(total_pairs, m=400, n_min=1000, n_max=50000, pool_reads=4000, seed=20261019 + 5)
+    pack = SeqPack()
+    for s in seqs:
+        pack.add_codes(s)
+    codes, offsets, lens = pack.finalize()
+    mine = slice(rank, total_pairs, world)
+    t_my, r_my = t_idx[mine], r_idx[mine]
+    batch = 65536
+    chunks = [(t_my[a:a + batch], r_my[a:a + batch]) for a in range(0, len(t_my), batch)]
+    cells_my = float((2 * 400 * lens[r_my].astype(np.int64)).sum())
+    log(f"[rank {rank}] pair sweep: {len(t_my)} of {total_pairs} pairs in {len(chunks)} batches, pool of {len(seqs)} sequences "
+        f"({codes.size / 1e6:.0f} MB), built in {time.time() - t0:.1f}s")
+    eng.ssw_check_batch(pack, chunks[0][0][:4096], chunks[0][1][:4096])      # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    outs = [eng.ssw_check_batch(pack, t, r) for t, r in chunks]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    red = torch.tensor([dt], dtype=torch.float64, device=dev)
+    tot = torch.tensor([cells_my, float(len(t_my))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    dt = float(red[0])
+    out = np.concatenate(outs)
+    entry = {"baseline_config": 5, "workload": "pair_sweep: m=400, reads 1-50 kb uniform, half carry the template at 8% error",
+             "pairs": int(tot[1]), "n_gpus": world, "s": dt, "gcups": float(tot[0]) / dt / 1e9, "pairs_per_s": float(tot[1]) / dt,
+             "hits": int((out["score"] > 480).sum()),
+             "note": "through nmsv_ssw_check_batch (both strands + begin pass) with host buffers: H2D of the pool per batch and "
+                     "D2H of the tuples are inside the time; max over ranks"}
+    if rank == 0:      # oracle on a sample of this rank's pairs
+        n = int(max(64, min(len(t_my), cpu_gcups * 1e9 * cpu_seconds / (2 * 400 * float(lens[r_my].mean())))))
+        n_t = int(lens.size)
+        tm = np.unique(t_my[:n])
+        rc_off, pos = [], int(codes.size)
+        extra = []
+        for t in tm:
+            tc = codes[int(offsets[t]):int(offsets[t]) + int(lens[t])]
+            extra.append(_COMP[tc[::-1]]); rc_off.append(pos); pos += len(tc)
+        rc_of = {int(t): n_t + k for k, t in enumerate(tm)}
+        c2 = np.concatenate([codes] + extra)
+        o2 = np.concatenate([offsets, np.asarray(rc_off, dtype=np.uint64)])
+        l2 = np.concatenate([lens, lens[tm]])
+        ti = np.stack([t_my[:n], np.array([rc_of[int(t)] for t in t_my[:n]], dtype=np.uint32)], axis=1).ravel()
+        ri = np.repeat(r_my[:n], 2)
+        res, _ = O.ssw_batch(c2, o2, l2, ti, ri, engine="striped", threads=threads)
+        job = OracleJob.__new__(OracleJob)
+        job.m = np.full(n, 400, dtype=np.int64)
+        exp = job.expected(res)
+        got = out[:n]
+        ok = np.ones(n, dtype=bool)
+        for name in ("score", "qstart", "qend", "tstart", "tend", "strand"):
+            ok &= (got[name] == exp[name]) | ((exp["score"] == 0) & (name != "score"))
+        entry["parity_sampled"] = {"checked": n, "equal": int(ok.sum())}
+        if int(ok.sum()) != n:
+            raise SystemExit(f"PARITY MISMATCH against the oracle on the pair sweep: {entry['parity_sampled']}")
+        log(f"[config 5] pair sweep: {entry['gcups']:.0f} GCUPS on {world} GPU(s), parity {int(ok.sum())}/{n}")
+    return entry
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -226,9 +439,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--svs-per-gpu", type=int, default=int(os.environ.get("NMSV_BENCH_SVS", "192")))
+    ap.add_argument("--svs-per-gpu", type=int, default=int(os.environ.get("NMSV_BENCH_SVS", "384")))
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU work per step of the baseline sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU-oracle leg (cpu_baseline and parity_sampled)")
+    ap.add_argument("--no-configs", action="store_true", help="headline workload only")
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs of the config-5 sweep (whole job, all ranks)")
+    ap.add_argument("--strong-svs", type=int, default=768, help="candidates of the fixed strong-scaling job (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
 
@@ -269,11 +485,9 @@ def main():
 
     # ---- device-resident hot path
     plan = eng.plan(pack, svs, reads)
-    plan.set_profiling(True)
     st = plan.stats()
     # the path's only exchange: ONE merge of the per-GPU supporting-read count tables at the end of the job
     # (NCCL all-reduce of a dense int32 table over NVLink); the job here = the timed steps
-    cap = len(svs) + 64
     n_max = torch.tensor([len(svs)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(n_max, op=dist.ReduceOp.MAX)
@@ -294,6 +508,7 @@ def main():
     final_gather()
     counts.zero_()
     barrier()
+    plan.set_profiling(True)                          # per-launch events of every timed step (no host sync between them)
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -305,7 +520,8 @@ def main():
     e1.record(stream)
     barrier()
     ms_step = e0.elapsed_time(e1) / args.steps
-    ktimes = plan.kernel_times()                      # launches of the last timed step
+    ktimes = plan.kernel_times()                      # mean over the timed steps
+    plan.set_profiling(False)
     checked, supporting, records = plan.download()
     st = plan.stats()
 
@@ -354,37 +570,45 @@ def main():
         final_gather()
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
-    assert all((s_ == supporting).all() and len(r_) == len(records) for _, s_, r_ in results), "pipelined e2e results differ"
+    assert all((s_ == supporting).all() and (r_ == records).all() for _, s_, r_ in results), "pipelined e2e results differ"
     clocks = sampler.stop()
-    assert (s_e2e == supporting).all() and len(r_e2e) == len(records), "e2e and device-resident results differ"
+    assert (s_e2e == supporting).all() and (r_e2e == records).all(), "e2e and device-resident results differ"
+    eng2.close()
 
     # ---- max over ranks, totals over ranks
     red = torch.tensor([ms_step, e2e_s, e2e_serial_s], dtype=torch.float64, device=dev)
-    tot = torch.tensor([st["cells_reference"], st["cells_executed"], n_cand, int(supporting.sum())],
+    tot = torch.tensor([st["cells_reference"], st["cells_executed"], n_cand, int(supporting.sum()), st["cells_pruned"]],
                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
     ms_step, e2e_s, e2e_serial_s = float(red[0]), float(red[1]), float(red[2])
-    cells_ref, cells_exec, cand_total, supp_total = [float(x) for x in tot]
+    cells_ref, cells_exec, cand_total, supp_total, cells_pruned = [float(x) for x in tot]
 
+    line = None
+    threads = os.cpu_count() or 1
     if rank == 0:
         fwd = [(r, ms) for name, r, ms in ktimes if name == "sw_forward"]
         dom_r, dom_ms = max(fwd, key=lambda x: x[1])
         step_kernel_ms = sum(ms for _, _, ms in ktimes)
         achieved = st["cells_executed"] * DPX_PER_CELL / (dom_ms * 1e-3)     # forward cells all run in this launch
         h2d = st["h2d_bytes"]
+        traffic, traffic_src = _traffic(st["cells_executed"])
         roofline = {
             "bound": "int_alu (DPX issue rate; not hbm, not tensor)",
-            "kernel": f"sw_wavefront_kernel<{dom_r}> (forward launch; it also drains the fused begin pass, whose cells are not counted)",
+            "kernel": f"sw_wavefront_kernel<{dom_r}> (forward launch; it also runs the queued reference-allele alignments and "
+                      f"the begin pass, whose cells are not counted)",
             "achieved": achieved / 1e12, "peak": dpx_peak / 1e12, "unit": "T DPX lane-inst/s",
             "frac": achieved / dpx_peak,
-            "peak_source": "measured live: register-only VIADDMNMX.S16x2 loop on this GPU (nmsv_measure_dpx_peak)",
+            "peak_source": "measured live: register-only VIADDMNMX.S16x2 loop on this GPU (nmsv_measure_dpx_peak); the ALU "
+                           "pipe issues one warp instruction per 2 clocks per scheduler",
+            "peak_nominal_int32": {"value": info["sm_count"] * 128 * info["sm_clock_khz"] * 1e3 / 1e12, "unit": "T lane-ops/s",
+                                   "note": "SMs x 128 INT32 lanes x clock (SURVEY 8d); DPX s16x2 is a half-rate pipe: 64 lanes/clk/SM"},
             "dpx_lane_inst_per_cell": DPX_PER_CELL,
-            "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / step_kernel_ms,
+            "kernel_ms": dom_ms, "kernel_ms_source": f"mean over the {args.steps} timed steps (CUDA events on the launching stream)",
+            "kernel_share_of_step": dom_ms / step_kernel_ms,
             "gcups_kernel": st["cells_executed"] / (dom_ms * 1e-3) / 1e9,
-            "traffic": _traffic(st["cells_executed"])[0],            # DRAM bytes per launch (ncu), or null
-            "traffic_source": _traffic(st["cells_executed"])[1],
+            "traffic": traffic, "traffic_source": traffic_src,
             "hbm": {"algorithmic_bytes": int(codes.size), "achieved_gbs": codes.size / (dom_ms * 1e-3) / 1e9,
                     "peak_gbs": _measured_peaks().get("hbm_gbs"), "note": "HBM is 3-4 orders of magnitude off the critical path"},
             "launches_ms": [{"kernel": n, "R": r, "ms": round(ms, 4)} for n, r, ms in ktimes],
@@ -398,10 +622,11 @@ def main():
                        "sv_candidates_per_gpu_per_step": n_cand, "reads_per_gpu_per_step": int(len(reads)),
                        "read_bases_per_gpu_mb": round(codes.size / 1e6, 1),
                        "l2": f"inputs ({codes.size / 1e6:.0f} MB of read bases per GPU) exceed the {info['l2_bytes'] / 1e6:.0f} MB L2",
-                       "parallelism": f"sv-shards x{world}, equal cell budget per GPU, one NCCL all-reduce of the count tables at the end of the job" if world > 1 else "single GPU"},
+                       "parallelism": f"sv-shards x{world}, equal planned cells per GPU, one NCCL all-reduce of the count tables at the end of the job" if world > 1 else "single GPU"},
             "sv_per_s": cand_total / (ms_step * 1e-3),
             "gcups_executed": cells_exec / (ms_step * 1e-3) / 1e9,
-            "cells_reference_per_step": cells_ref, "cells_executed_per_step": cells_exec,
+            "cells_reference_per_step": cells_ref, "cells_executed_per_step": cells_exec, "cells_pruned_per_step": cells_pruned,
+            "reads_pruned_per_gpu_per_step": st["reads_pruned"],
             "supporting_reads_per_step": supp_total,
             "clocks": clocks,
             "e2e": {"value": cells_ref / e2e_s / 1e9, "unit": "GCUPS", "ms_per_step": e2e_s * 1e3,
@@ -413,29 +638,73 @@ def main():
             "roofline": roofline,
             "device": info["name"],
         }
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            sp, t, r, cells, _ = cpu_sample(pack, svs, reads, 2e10)
-            dt, used = run_cpu(sp, t, r, threads)
-            sp, t, r, cells, n_used = cpu_sample(pack, svs, reads, max(2e10, cells / dt * 15.0))
-            dt, used = run_cpu(sp, t, r, threads)
-            line["cpu_baseline"] = {
-                "value": cells / dt / 1e9, "unit": "GCUPS", "cores": used, "kind": "port",
-                "sample": f"{n_used} SV candidates of the same batch (tumor reads), {len(t)} alignments with "
-                          f"reversed begin pass, {cells / 1e9:.1f} G forward cells in {dt:.1f}s; engine oracle/nmsv_striped.c "
-                          f"(AVX2 striped, 8-bit then 16-bit: parasail-equivalent port, parasail not installable)"}
-        emit(line)
     plan.close()
+
+    # ---- CPU leg on rank 0 at N = 1: the timed baseline, whose results are the oracle of the sampled parity check
+    cpu_gcups = 80.0
+    parity = {}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        job = OracleJob(pack, svs, reads, 2e10)
+        dt, used, _ = job.run(threads)
+        job = OracleJob(pack, svs, reads, max(2e10, job.cells / dt * 15.0))
+        dt, used, res = job.run(threads)
+        cpu_gcups = job.cells / dt / 1e9
+        line["cpu_baseline"] = {
+            "value": cpu_gcups, "unit": "GCUPS", "cores": used, "kind": "port",
+            "sample": f"{job.n_svs} SV candidates of the same batch (tumor reads), {len(job.t_idx)} alignments with "
+                      f"reversed begin pass, {job.cells / 1e9:.1f} G forward cells in {dt:.1f}s; engine oracle/nmsv_striped.c "
+                      f"(AVX2 striped, 8-bit then 16-bit: parasail-equivalent port, parasail not installable)"}
+        parity[WORKLOAD] = parity_validate(eng, pack, svs, reads, job, res, supporting)
+        log(f"[config 2] parity {parity[WORKLOAD]['equal']}/{parity[WORKLOAD]['checked']} alignments equal the oracle")
+
+    # ---- the other BASELINE configs
+    configs = []
+    if not args.no_configs:
+        if world == 1 and rank == 0:
+            configs.append({"baseline_config": 2, "workload": WORKLOAD, "sv_candidates": n_cand, "ms": ms_step,
+                            "sv_per_s": line["sv_per_s"], "gcups": line["value"], "gcups_executed": line["gcups_executed"],
+                            "roofline": {"frac": line["roofline"]["frac"]}, "note": "the headline measurement of this line"})
+            for number, preset, n_sv, over in SHAPES:
+                if args.no_cpu_baseline:
+                    continue
+                configs.append(shape_entry(torch, stream, eng, dpx_peak, number, preset, n_sv, over, cpu_gcups, 3.0, threads))
+                parity[preset] = configs[-1]["parity_sampled"]
+        sweep = pair_sweep_entry(torch, dist, dev, eng, rank, world, args.pairs, cpu_gcups, 0.0 if args.no_cpu_baseline else 3.0, threads)
+        if rank == 0:
+            configs.append(sweep)
+            if "parity_sampled" in sweep:
+                parity["pair_sweep"] = sweep["parity_sampled"]
+        if world > 1:
+            strong = _strong(torch, dist, dev, eng, rank, world, args)
+            if rank == 0:
+                line["strong"] = strong
+    if rank == 0:
+        configs.sort(key=lambda c: c["baseline_config"])
+        line["configs"] = configs
+        if parity:
+            line["parity_sampled"] = {"checked": sum(p["checked"] for p in parity.values()),
+                                      "equal": sum(p["equal"] for p in parity.values()),
+                                      "oracle": "oracle/nmsv_striped.c + the strand rule of ssw_check; the CUDA results of the same "
+                                                "reads (a plan that computes every alignment) are compared field by field",
+                                      "per_config": parity}
+        emit(line)
+    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _strong(torch, dist, dev, eng, rank, world, args):
+    from bench_strong import strong_scaling
+    return strong_scaling(torch, dist, dev, eng, rank, world, args.strong_svs)
+
+
 def _traffic(cells_executed: float):
-    """DRAM bytes of the forward launch: ncu capture under profiles/, scaled by the executed cells of this batch
-    (the traffic is the per-column tile-boundary spill, proportional to the cells). None if the capture is absent."""
+    """DRAM bytes of the forward launch. Not measurable inside a run (ncu replays kernels): the figure comes from the
+    committed ncu capture of the same kernel on the 192-candidate batch, scaled by the executed cells (the traffic is
+    the read bases, proportional to the cells at a fixed template length)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_final_traffic.json")))
-        return t["dram_bytes_per_executed_cell"] * cells_executed, t["source"] + ", scaled by executed cells"
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        return t["dram_bytes_per_executed_cell"] * cells_executed, "from capture: " + t["source"] + ", scaled by executed cells"
     except Exception:   # noqa: BLE001
         return None, None
 

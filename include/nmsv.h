@@ -151,6 +151,7 @@ typedef struct {
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
 int nmsv_abi_version(void);
+int nmsv_device_count(void);                          /* usable CUDA devices (0: none) */
 int nmsv_create(nmsv_ctx **ctx, int device);          /* one ctx per process/GPU (mirrors --processes, run.py:367) */
 void nmsv_destroy(nmsv_ctx *ctx);
 const char *nmsv_last_error(const nmsv_ctx *ctx);     /* ctx may be NULL: error of a failed nmsv_create */
@@ -205,7 +206,9 @@ int nmsv_plan_download(nmsv_plan *plan, int32_t *checked, int32_t *supporting, n
                        uint64_t record_capacity, uint64_t *n_records);
 int nmsv_plan_stats(const nmsv_plan *plan, nmsv_stats *stats);
 /* measurement hooks: per-launch durations by CUDA events recorded on the launching stream (phase: 0 plan, 1 forward
- * wavefront, 2 decide, 3 begin-pass wavefront, 4 final; rclass = strip height R of a wavefront launch) */
+ * wavefront, 2 decide, 3 follow-up wavefront launch over the dynamic queue, 4 final; rclass = strip height R of a
+ * wavefront launch). nmsv_plan_kernel_times returns the MEAN over the runs since nmsv_plan_set_profiling(plan, 1)
+ * (the last 32 at most); it waits for those runs, nmsv_plan_run itself never synchronises. */
 int nmsv_plan_set_profiling(nmsv_plan *plan, int on);
 int nmsv_plan_kernel_times(nmsv_plan *plan, float *ms, uint32_t *phase, uint32_t *rclass, uint32_t capacity,
                            uint32_t *n_launches);

@@ -61,7 +61,7 @@ class Stats(ctypes.Structure):
 
 ABI_VERSION = 2
 
-EXPORTS = ["nmsv_abi_version", "nmsv_create", "nmsv_destroy", "nmsv_last_error", "nmsv_set_stream", "nmsv_set_option",
+EXPORTS = ["nmsv_abi_version", "nmsv_device_count", "nmsv_create", "nmsv_destroy", "nmsv_last_error", "nmsv_set_stream", "nmsv_set_option",
            "nmsv_device_info", "nmsv_encode_ascii", "nmsv_encode_pack", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
            "nmsv_plan_create", "nmsv_plan_run", "nmsv_plan_download", "nmsv_plan_stats", "nmsv_plan_download_alns",
            "nmsv_plan_destroy", "nmsv_plan_set_profiling", "nmsv_plan_kernel_times", "nmsv_plan_copy_counts_device",
@@ -102,6 +102,7 @@ def load() -> ctypes.CDLL:
     L.nmsv_abi_version.restype = ctypes.c_int
     if L.nmsv_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path} has ABI version {L.nmsv_abi_version()}, this package needs {ABI_VERSION}")
+    L.nmsv_device_count.restype = ctypes.c_int
     L.nmsv_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
     L.nmsv_create.restype = ctypes.c_int
     L.nmsv_destroy.argtypes = [vp]

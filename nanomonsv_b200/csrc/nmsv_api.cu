@@ -165,6 +165,12 @@ static void fill_packed(SwParams& sp)
 
 extern "C" int nmsv_abi_version(void) { return NMSV_ABI_VERSION; }
 
+extern "C" int nmsv_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
 extern "C" const char* nmsv_last_error(const nmsv_ctx* ctx)
 {
     return ctx ? ctx->error.c_str() : g_create_error.c_str();
@@ -878,24 +884,26 @@ struct nmsv_plan {
     std::vector<int32_t> checked;
     nmsv_stats stats{};
     bool ran = false;
-    // per-launch CUDA-event timing (nmsv_plan_set_profiling): events are recorded on the launching stream
+    // per-launch CUDA-event timing (nmsv_plan_set_profiling): events are recorded on the launching stream; the last
+    // kProfRuns runs keep their own events, so that the durations can be averaged over the runs of a timed region
+    // without a host synchronisation between them
+    static constexpr uint32_t kProfRuns = 32, kProfSlots = 40;
     bool profiling = false;
-    std::vector<cudaEvent_t> events;
+    uint32_t prof_runs = 0;            // runs recorded since profiling was switched on
+    std::vector<cudaEvent_t> events;   // [kProfRuns][kProfSlots], created on demand
     std::vector<uint32_t> launch_phase, launch_rclass;
-    ~nmsv_plan() { for (cudaEvent_t e : events) cudaEventDestroy(e); }
+    ~nmsv_plan() { for (cudaEvent_t e : events) if (e) cudaEventDestroy(e); }
 };
 
 enum : uint32_t { kPhasePlan = 0, kPhaseFwd = 1, kPhaseDecide = 2, kPhaseRev = 3, kPhaseFinal = 4 };
 
 static void mark(nmsv_plan* pl, size_t& slot, cudaStream_t s)
 {
-    if (!pl->profiling) return;
-    if (slot >= pl->events.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        pl->events.push_back(e);
-    }
-    cudaEventRecord(pl->events[slot++], s);
+    if (!pl->profiling || slot >= nmsv_plan::kProfSlots) return;
+    if (pl->events.empty()) pl->events.assign((size_t)nmsv_plan::kProfRuns * nmsv_plan::kProfSlots, nullptr);
+    cudaEvent_t& e = pl->events[(size_t)(pl->prof_runs % nmsv_plan::kProfRuns) * nmsv_plan::kProfSlots + slot++];
+    if (!e) cudaEventCreate(&e);
+    cudaEventRecord(e, s);
 }
 
 extern "C" void nmsv_plan_destroy(nmsv_plan* plan)
@@ -1175,6 +1183,7 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     fp.record_capacity = n_reads; fp.counters = dp.counters;
     final_kernel<<<(n_reads + tpb - 1) / tpb, tpb, 0, s>>>(fp);
     note(kPhaseFinal, 0); mark(pl, ev, s);
+    if (pl->profiling) pl->prof_runs += 1;
     CUDA_TRY(ctx, cudaGetLastError());
     return NMSV_OK;
 }
@@ -1183,6 +1192,7 @@ extern "C" int nmsv_plan_set_profiling(nmsv_plan* pl, int on)
 {
     if (!pl) return NMSV_E_INVALID;
     pl->profiling = on != 0;
+    pl->prof_runs = 0;
     return NMSV_OK;
 }
 
@@ -1193,13 +1203,23 @@ extern "C" int nmsv_plan_kernel_times(nmsv_plan* pl, float* ms, uint32_t* phase,
     nmsv_ctx* ctx = pl->ctx;
     const uint32_t n = (uint32_t)pl->launch_phase.size();
     *n_launches = n;
-    if (!pl->profiling || !pl->ran || pl->events.size() < (size_t)n + 1)
+    if (!pl->profiling || !pl->ran || pl->prof_runs == 0 || n + 1 > nmsv_plan::kProfSlots)
         return set_err(ctx, NMSV_E_INVALID, "nmsv_plan_kernel_times needs a run with profiling enabled");
     if (capacity < n) return set_err(ctx, NMSV_E_CAPACITY, "kernel time buffers hold %u entries, %u launches", capacity, n);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, cudaEventSynchronize(pl->events[n]));
+    const uint32_t runs = std::min(pl->prof_runs, nmsv_plan::kProfRuns);
+    std::vector<double> sum(n, 0.0);
+    for (uint32_t k = 0; k < runs; ++k) {
+        const size_t base = (size_t)((pl->prof_runs - 1 - k) % nmsv_plan::kProfRuns) * nmsv_plan::kProfSlots;
+        CUDA_TRY(ctx, cudaEventSynchronize(pl->events[base + n]));
+        for (uint32_t i = 0; i < n; ++i) {
+            float t = 0.f;
+            CUDA_TRY(ctx, cudaEventElapsedTime(&t, pl->events[base + i], pl->events[base + i + 1]));
+            sum[i] += t;
+        }
+    }
     for (uint32_t i = 0; i < n; ++i) {
-        if (ms) CUDA_TRY(ctx, cudaEventElapsedTime(&ms[i], pl->events[i], pl->events[i + 1]));
+        if (ms) ms[i] = (float)(sum[i] / runs);
         if (phase) phase[i] = pl->launch_phase[i];
         if (rclass) rclass[i] = pl->launch_rclass[i];
     }

@@ -320,10 +320,25 @@ class Engine:
 _default_engine: Optional[Engine] = None
 
 
+def pick_device() -> int:
+    """The GPU of this process: NMSV_DEVICE, else LOCAL_RANK (torchrun: one process per GPU), else the worker's place in
+    a multiprocessing pool -- the reference runs its `--processes N` shards in a multiprocessing.Pool (run.py:361-372),
+    whose workers are numbered 1..N: worker k takes GPU (k - 1) mod #GPUs, so N = 8 workers spread over 8 GPUs."""
+    import os
+    for var in ("NMSV_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(var, "") != "":
+            return int(os.environ[var])
+    import multiprocessing
+    ident = getattr(multiprocessing.current_process(), "_identity", ())
+    n_dev = _lib.load().nmsv_device_count()
+    if ident and n_dev > 0:
+        return (int(ident[0]) - 1) % n_dev
+    return 0
+
+
 def default_engine() -> Engine:
-    """Process-wide engine on the GPU selected by LOCAL_RANK (one process per GPU) or device 0."""
+    """Process-wide engine on the GPU chosen by pick_device()."""
     global _default_engine
     if _default_engine is None:
-        import os
-        _default_engine = Engine(int(os.environ.get("NMSV_DEVICE", os.environ.get("LOCAL_RANK", "0"))))
+        _default_engine = Engine(pick_device())
     return _default_engine

@@ -1,6 +1,7 @@
 """Multi-GPU sharding of a validation job: SV candidates are independent, so they are partitioned across the
-ranks (one process per GPU) with no communication during compute, and the per-SV counts are merged by ONE
-collective at the end (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+ranks (one process per GPU) with no communication during compute; at the end the per-SV counts are merged by ONE
+all-reduce and the supporting-read records by a count all-gather plus one padded all-gather (NCCL over NVLink on the
+GPU box, gloo in the CPU tests).
 
 The reference's own parallelism is the same shape: `--processes N` deals clusters round-robin into N shard files,
 runs them in a process pool and concatenates the text outputs (run.py:324-379, :391-407).
@@ -68,26 +69,60 @@ def merge_counts(n_total: int, local_indices: Sequence[int], local_checked: np.n
     return table.cpu().numpy()
 
 
-def gather_records(local_lines: List[str], group=None) -> List[str]:
-    """Variable-size supporting-read info lines of all ranks, in rank order (all_gather_object: host side)."""
+RECORD_COLS = 2 + 24     # SV index in the whole job, read ordinal inside the SV, 4 x (score, qstart, qend, tstart, tend, strand)
+
+
+def records_to_rows(records: np.ndarray, svs: np.ndarray, global_sv_ids: Sequence[int]) -> np.ndarray:
+    """nmsv_record[] of one rank's batch -> int32 rows that mean the same on every rank: the SV's index in the whole job
+    and the read's ordinal inside its SV instead of batch-local indices."""
+    rows = np.zeros((len(records), RECORD_COLS), dtype=np.int32)
+    if len(records):
+        sv_local = records["sv"].astype(np.int64)
+        rows[:, 0] = np.asarray(global_sv_ids, dtype=np.int64)[sv_local]
+        rows[:, 1] = records["read"].astype(np.int64) - svs["read_begin"][sv_local].astype(np.int64)
+        rows[:, 2:] = records["aln"].view(np.int32).reshape(len(records), 24)
+    return rows
+
+
+def gather_record_rows(rows: np.ndarray, group=None, device=None) -> np.ndarray:
+    """Supporting-read records of all ranks: one all-gather of the per-rank counts, then one padded all-gather of the
+    int32 rows (on the device over NCCL, on CPU tensors over gloo). Returned sorted by (SV, read): identical on every
+    rank and independent of the partition."""
+    import torch
     import torch.distributed as dist
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return list(local_lines)
-    out: List[Optional[List[str]]] = [None] * dist.get_world_size(group)
-    dist.all_gather_object(out, list(local_lines), group=group)
-    return [ln for part in out for ln in (part or [])]
+    rows = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, RECORD_COLS)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        dev = device or "cpu"
+        n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, n, group=group)
+        cap = max(int(counts.max().item()), 1)
+        mine = torch.zeros((cap, RECORD_COLS), dtype=torch.int32, device=dev)
+        if rows.shape[0]:
+            mine[:rows.shape[0]] = torch.from_numpy(rows).to(dev)
+        everything = torch.zeros((world, cap, RECORD_COLS), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(everything.view(-1), mine.view(-1), group=group)
+        everything, counts = everything.cpu().numpy(), counts.cpu().numpy()
+        rows = np.concatenate([everything[r, :int(counts[r])] for r in range(world)], axis=0)
+    order = np.lexsort((rows[:, 1], rows[:, 0]))
+    return rows[order]
 
 
 def validate_sharded(costs: Sequence[float], run_local, rank: int, world: int, group=None, device=None,
                      partition: str = "lpt"):
     """Partition n = len(costs) SV candidates over `world` ranks, run `run_local(indices)` on this rank's share
-    (-> (checked[int], supporting[int], info_lines[str]) for those indices, in order) and merge: returns the dense
-    (n, 2) count table and all info lines, identical on every rank. `run_local` is the GPU path in production
-    (Alignment_counter on this rank's engine); the collective is the only communication."""
+    (-> (checked[int], supporting[int], record rows[int32, RECORD_COLS]) for those indices, column 0 = index in the
+    whole job) and merge: returns the dense (n, 2) count table, the record rows of the whole job sorted by (SV, read)
+    -- both identical on every rank -- and the partition. `run_local` is the GPU path in production (this rank's
+    engine); the two collectives are the only communication."""
     n = len(costs)
     parts = lpt_partition(costs, world) if partition == "lpt" else round_robin_partition(n, world)
     mine = parts[rank]
-    checked, supporting, lines = run_local(mine) if mine else ([], [], [])
+    if mine:
+        checked, supporting, rows = run_local(mine)
+    else:
+        checked, supporting, rows = [], [], np.zeros((0, RECORD_COLS), dtype=np.int32)
     table = merge_counts(n, mine, np.asarray(checked, dtype=np.int32), np.asarray(supporting, dtype=np.int32),
                          group=group, device=device)
-    return table, gather_records(list(lines), group=group), parts
+    return table, gather_record_rows(rows, group=group, device=device), parts

@@ -204,3 +204,26 @@ def test_byte_level_seam_reader_builds_the_same_batches(tmp_path, monkeypatch, s
         open(seam, "a").write("\nbroken line without tabs\n")
         monkeypatch.setenv("NMSV_SEAM_READER", "bytes")
         C.count_sread_from_seam(seam, fc, fi, wl.fasta, sbnd, 40, 1.2, engine=_RecordingEngine())
+
+
+def test_device_pick_follows_env_then_pool_worker(monkeypatch):
+    """default_engine(): NMSV_DEVICE, then LOCAL_RANK, then the multiprocessing-pool worker number modulo the number of
+    GPUs (the reference's --processes pool, run.py:361-372), then 0."""
+    import multiprocessing
+    from nanomonsv_b200 import engine
+    monkeypatch.delenv("NMSV_DEVICE", raising=False)
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+    assert engine.pick_device() == 0
+    monkeypatch.setenv("LOCAL_RANK", "3")
+    assert engine.pick_device() == 3
+    monkeypatch.setenv("NMSV_DEVICE", "5")
+    assert engine.pick_device() == 5
+    monkeypatch.delenv("NMSV_DEVICE")
+    monkeypatch.delenv("LOCAL_RANK")
+
+    class FakeLib:
+        def nmsv_device_count(self):
+            return 8
+    monkeypatch.setattr(engine._lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(multiprocessing.current_process(), "_identity", (11,), raising=False)
+    assert engine.pick_device() == (11 - 1) % 8

@@ -48,6 +48,17 @@ def _free_port():
     return port
 
 
+def _rows_of(i, seam_rows_i, info_lines):
+    """Oracle info lines of SV i -> the int32 record rows that the GPU path gathers (shard.RECORD_COLS)."""
+    ids = [r[0] for r in seam_rows_i]
+    rows = []
+    for line in info_lines:
+        f = line.split("\t")
+        vals = [0 if x == "None" else (1 if x == "+" else (-1 if x == "-" else int(x))) for x in f[9:]]
+        rows.append([i, ids.index(f[8])] + vals)
+    return np.asarray(rows, dtype=np.int32).reshape(-1, shard.RECORD_COLS)
+
+
 def _worker(rank, world, port, seam_rows, contigs, keys, costs, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -55,16 +66,16 @@ def _worker(rank, world, port, seam_rows, contigs, keys, costs, out):
     fasta = O.DictFasta(contigs)
 
     def run_local(indices):
-        checked, supporting, lines = [], [], []
+        checked, supporting, rows = [], [], [np.zeros((0, shard.RECORD_COLS), dtype=np.int32)]
         for i in indices:
             count_line, info = O.count_one_sv(keys[i], seam_rows[i], fasta, var_read_min_mapq=0, engine="striped")
             f = count_line.split("\t")
-            checked.append(int(f[-2])); supporting.append(int(f[-1])); lines += info
-        return checked, supporting, lines
+            checked.append(int(f[-2])); supporting.append(int(f[-1])); rows.append(_rows_of(i, seam_rows[i], info))
+        return checked, supporting, np.concatenate(rows)
 
-    table, lines, parts = shard.validate_sharded(costs, run_local, rank, world)
+    table, rows, parts = shard.validate_sharded(costs, run_local, rank, world)
     if rank == 0:
-        out.put((table.tolist(), sorted(lines), parts))
+        out.put((table.tolist(), rows.tolist(), parts))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -81,21 +92,22 @@ def test_two_rank_gloo_merge_equals_single_process():
     costs = [sum(len(r[3]) for r in rows) for rows in seam_rows]
     # single process truth
     fasta = O.DictFasta(contigs)
-    exp_table, exp_lines = [], []
-    for k, rows in zip(keys, seam_rows):
+    exp_table, exp_rows = [], []
+    for i, (k, rows) in enumerate(zip(keys, seam_rows)):
         cl, info = O.count_one_sv(k, rows, fasta, var_read_min_mapq=0, engine="striped")
         exp_table.append([int(cl.split("\t")[-2]), int(cl.split("\t")[-1])])
-        exp_lines += info
+        exp_rows += _rows_of(i, rows, info).tolist()
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, seam_rows, contigs, keys, costs, out)) for r in range(2)]
     for p in procs:
         p.start()
-    table, lines, parts = out.get(timeout=240)
+    table, rows, parts = out.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert table == exp_table
-    assert lines == sorted(exp_lines)
+    # records of all ranks, gathered with a count all-gather + one padded all-gather, sorted by (SV, read)
+    assert len(exp_rows) >= 3 and rows == sorted(exp_rows, key=lambda r: (r[0], r[1]))
     assert sorted(i for p in parts for i in p) == list(range(7)) and all(parts)
