@@ -122,6 +122,7 @@ def build_batch(n_sv: int, rank: int, args=None, preset: str = WORKLOAD, budget:
             for rd in wl.samples[sample][i]:
                 bb.add_read(rd.codes, rd.mapq1, None if is_sbnd else rd.mapq2)
     pack, svs, reads = bb.finalize()
+    build_batch.last = (wl, [j for j in wl.sv_order() if j in keep_set])      # for the stage-seam measurement
     log(f"[rank {rank}] {preset}: {len(keep)} candidates x (tumor, control), {len(reads)} reads, "
         f"{pack.finalize()[0].size / 1e6:.0f} MB of bases, built in {time.time() - t0:.1f}s")
     return cfg, pack, svs, reads
@@ -235,6 +236,53 @@ def parity_validate(eng, pack, svs, reads, job: OracleJob, res, full_counts=None
         bad = np.flatnonzero(~ok)[:5]
         raise SystemExit(f"PARITY MISMATCH against the oracle: {out}; first rows {[(int(job.rows[b]), int(job.slots[b])) for b in bad]}")
     return out
+
+
+def stage_seam_e2e(eng, wl, order, n_cand, checked, supporting, n_records) -> dict:
+    """The drop-in stage function itself (count_sread_from_seam = count_sread_by_alignment after the read gathering,
+    reference :414-448) on seam TSVs written before the timer: parsing, group-by, template construction, packing,
+    H2D, kernels, D2H and the two output files per sample, tumor then control like `nanomonsv get`. The files are held
+    to the device-resident results of the same candidates."""
+    import shutil
+    import tempfile
+    from nanomonsv_b200 import count_sread_by_alignment as C
+    from nanomonsv_b200 import synth
+    tmp = tempfile.mkdtemp(prefix="nmsv_stage_")
+    try:
+        seams, size = {}, 0
+        for sample in ("tumor", "control"):
+            seams[sample] = os.path.join(tmp, sample + ".seam.tsv")
+            with open(seams[sample], "w") as h:
+                for i in order:
+                    key = wl.svs[i].key
+                    for rd in wl.samples[sample][i]:
+                        h.write(f"{key}\t{rd.rid}\t{rd.mapq1}\t{rd.mapq2}\t{synth.codes_to_str(rd.codes)}\n")
+            size += os.path.getsize(seams[sample])
+        L = wl.config.validate_sequence_length
+
+        def run():
+            t0 = time.perf_counter()
+            for sample in ("tumor", "control"):
+                C.count_sread_from_seam(seams[sample], seams[sample] + ".count", seams[sample] + ".info", wl.fasta, False, 0,
+                                        1.2, engine=eng, validate_sequence_length=L)
+            return time.perf_counter() - t0
+        run()                       # warm-up (page cache, pools)
+        dt = min(run(), run())
+        got_c, got_s, n_info = [], [], 0
+        for sample in ("tumor", "control"):
+            for line in open(seams[sample] + ".count"):
+                f = line.rstrip("\n").split("\t")
+                got_c.append(int(f[-2])); got_s.append(int(f[-1]))
+            n_info += sum(1 for _ in open(seams[sample] + ".info"))
+        same = got_c == [int(x) for x in checked] and got_s == [int(x) for x in supporting] and n_info == n_records
+        if not same:
+            raise SystemExit("stage seam: the files written by count_sread_from_seam differ from the device-resident results")
+        return {"sv_per_s": n_cand / dt, "s": dt, "seam_bytes": size, "seam_gb_per_s": size / dt / 1e9,
+                "files_equal_device_resident_results": same,
+                "what": "count_sread_from_seam(tumor) + (control): seam TSV on disk (page cache) -> sread_count / sread_info files; "
+                        "one Python process, one GPU; nmsv_seam_scan + nmsv_encode_pack on the host, GPU batches on a worker thread"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -475,6 +523,7 @@ def main():
     dpx_peak = eng.measure_dpx_peak()
 
     cfg, pack, svs, reads = build_batch(args.svs_per_gpu, rank, args)
+    head_wl, head_order = build_batch.last
     codes, offsets, lens = pack.finalize()
     n_cand = len(svs) // 2
 
@@ -639,6 +688,10 @@ def main():
             "device": info["name"],
         }
     plan.close()
+    if rank == 0 and world == 1:
+        line["e2e_stage"] = stage_seam_e2e(eng, head_wl, head_order, n_cand, checked, supporting, len(records))
+        log(f"[stage seam] {line['e2e_stage']['sv_per_s']:.0f} candidates/s through count_sread_from_seam "
+            f"({line['e2e_stage']['seam_gb_per_s']:.2f} GB/s of seam TSV) vs {line['sv_per_s']:.0f}/s device resident")
 
     # ---- CPU leg on rank 0 at N = 1: the timed baseline, whose results are the oracle of the sampled parity check
     cpu_gcups = 80.0

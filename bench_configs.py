@@ -52,7 +52,7 @@ def main():
         return best, out
 
     plans = [("testdata_shaped", dict(n_sv=60)), ("colo829_shaped", dict(n_sv=40, contig_len=2_000_000, n_contigs=2)),
-             ("insertion_heavy", dict(n_sv=24, contig_len=2_000_000, n_contigs=2)),
+             ("insertion_heavy", dict(n_sv=int(os.environ.get("NMSV_BC_INS", "24")), contig_len=2_000_000, n_contigs=2)),
              ("single_breakend", dict(n_sv=300, contig_len=2_000_000, n_contigs=2))]
     only = set(args.only.split(",")) if args.only else None
     for name, kw in plans:

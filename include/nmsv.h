@@ -45,6 +45,9 @@ extern "C" {
 #define NMSV_E_INTERNAL (-5)  /* device-side consistency check failed */
 
 #define NMSV_NONE 0xFFFFFFFFu /* "no template in this slot" */
+#define NMSV_SEQ_ABSENT 0xFFFFFFFFFFFFFFFFull /* offsets[s]: only the LENGTH of sequence s is supplied. Legal for the sequence of
+                                  a read whose mapq test fails while the "prune" option is on: such a read is counted and
+                                  never aligned, so the caller need not encode or upload it. */
 #define NMSV_MAPQ_NONE (-1)   /* Python None in the seam TSV (count_sread_by_alignment.py:50,288) */
 
 #define NMSV_SLOT_VAR1 0
@@ -114,7 +117,7 @@ typedef struct {
 } nmsv_sv;
 
 typedef struct {
-    uint32_t seq;   /* sequence index of the read */
+    uint32_t seq;   /* sequence index of the read (its offsets[] entry may be NMSV_SEQ_ABSENT, see there) */
     uint32_t sv;    /* index of its SV in the svs array */
     int32_t mapq1;  /* NMSV_MAPQ_NONE = None */
     int32_t mapq2;
@@ -174,6 +177,40 @@ void nmsv_encode_ascii(const char *ascii, uint64_t n, uint8_t *codes);
  * count_sread_by_alignment.py:109-111): sequence i = src[src_off[i], +lens[i]) goes to dst[dst_off[i], ...); host only */
 void nmsv_encode_pack(const char *src, const uint64_t *src_off, const uint32_t *lens, const uint64_t *dst_off,
                       uint64_t n_seqs, uint8_t *dst);
+/* the same with every sequence padded by the wildcard code to the next 16-byte boundary (dst_off[] 16-byte aligned):
+ * the destination needs no pre-fill */
+void nmsv_encode_pack_padded(const char *src, const uint64_t *src_off, const uint32_t *lens, const uint64_t *dst_off,
+                             uint64_t n_seqs, uint8_t *dst);
+
+/* ---- host side of the stage seam: the group-by of count_sread_by_alignment.py:414-448 ------------------------------ */
+/* One pass over the key-sorted seam TSV (`key \t read id \t mapq1 \t mapq2 \t sequence`, :111,:120) held in memory
+ * (a mapping of the file): consecutive lines with the same key form a group (one SV candidate); inside a group the
+ * reference's dict semantics are applied (read id = first blank-separated token, pyssw.py:41; the last record of an id
+ * gives its mapq, its sequence is the last non-empty one, an id without any sequence is dropped; "None" = NMSV_MAPQ_NONE;
+ * is_sbnd: mapq2 is None). Whole groups are consumed from `start` until at least max_bases read bases are collected or a
+ * buffer is full; *next is where the next call starts. All offsets point into `data`: the caller encodes the sequences
+ * straight from there with nmsv_encode_pack. Host only, no ctx. NMSV_E_INVALID: malformed line at *error_off;
+ * NMSV_E_CAPACITY: the first group alone does not fit the buffers. */
+typedef struct {
+    uint64_t key_off;      /* the key column of the group */
+    uint32_t key_len;
+    uint32_t read_begin;   /* reads[read_begin .. read_end) in first-seen order */
+    uint32_t read_end;
+    uint32_t reserved;
+} nmsv_seam_group;
+
+typedef struct {
+    uint64_t id_off;
+    uint64_t seq_off;      /* stripped sequence */
+    uint32_t id_len;
+    uint32_t seq_len;
+    int32_t mapq1;
+    int32_t mapq2;
+} nmsv_seam_read;
+
+int nmsv_seam_scan(const char *data, uint64_t size, uint64_t start, uint64_t max_bases, int is_sbnd,
+                   nmsv_seam_group *groups, uint32_t group_cap, nmsv_seam_read *reads, uint32_t read_cap,
+                   uint32_t *n_groups, uint32_t *n_reads, uint64_t *next, uint64_t *error_off);
 
 /* ---- operator seam: batched parasail.ssw ---------------------------------------------------------------------- */
 int nmsv_ssw_batch(nmsv_ctx *ctx, const uint8_t *codes, uint64_t n_codes, const uint64_t *offsets,

@@ -14,6 +14,7 @@ import numpy as np
 from . import build as _build
 
 NMSV_NONE = 0xFFFFFFFF
+SEQ_ABSENT = 0xFFFFFFFFFFFFFFFF
 MAPQ_NONE = -1
 SV_SHORT_DEL_DUP = 1
 SV_SBND = 2
@@ -28,6 +29,11 @@ SV_DTYPE = np.dtype([("tmpl", "<u4", (4,)), ("tmpl_rc", "<u4", (4,)), ("read_beg
                      ("score_min", "<i4", (2,)), ("qstart_max", "<i4", (2,)), ("qend_min", "<i4", (2,)),
                      ("margin", "<i4"), ("min_mapq", "<i4"), ("flags", "<u4"), ("reserved", "<u4")])
 READ_DTYPE = np.dtype([("seq", "<u4"), ("sv", "<u4"), ("mapq1", "<i4"), ("mapq2", "<i4")])
+SEAM_GROUP_DTYPE = np.dtype([("key_off", "<u8"), ("key_len", "<u4"), ("read_begin", "<u4"), ("read_end", "<u4"),
+                             ("reserved", "<u4")])
+SEAM_READ_DTYPE = np.dtype([("id_off", "<u8"), ("seq_off", "<u8"), ("id_len", "<u4"), ("seq_len", "<u4"),
+                            ("mapq1", "<i4"), ("mapq2", "<i4")])
+assert SEAM_GROUP_DTYPE.itemsize == 24 and SEAM_READ_DTYPE.itemsize == 32
 RECORD_DTYPE = np.dtype([("read", "<u4"), ("sv", "<u4"), ("aln", ALN_DTYPE, (4,))])
 assert SV_DTYPE.itemsize == 80 and READ_DTYPE.itemsize == 16 and RECORD_DTYPE.itemsize == 104
 
@@ -62,7 +68,7 @@ class Stats(ctypes.Structure):
 ABI_VERSION = 2
 
 EXPORTS = ["nmsv_abi_version", "nmsv_device_count", "nmsv_create", "nmsv_destroy", "nmsv_last_error", "nmsv_set_stream", "nmsv_set_option",
-           "nmsv_device_info", "nmsv_encode_ascii", "nmsv_encode_pack", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
+           "nmsv_device_info", "nmsv_encode_ascii", "nmsv_encode_pack", "nmsv_encode_pack_padded", "nmsv_seam_scan", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
            "nmsv_plan_create", "nmsv_plan_run", "nmsv_plan_download", "nmsv_plan_stats", "nmsv_plan_download_alns",
            "nmsv_plan_destroy", "nmsv_plan_set_profiling", "nmsv_plan_kernel_times", "nmsv_plan_copy_counts_device",
            "nmsv_measure_dpx_peak", "nmsv_sw_jump_batch"]
@@ -120,6 +126,11 @@ def load() -> ctypes.CDLL:
     L.nmsv_encode_ascii.restype = None
     L.nmsv_encode_pack.argtypes = [vp, vp, vp, vp, u64, vp]
     L.nmsv_encode_pack.restype = None
+    L.nmsv_encode_pack_padded.argtypes = [vp, vp, vp, vp, u64, vp]
+    L.nmsv_encode_pack_padded.restype = None
+    L.nmsv_seam_scan.argtypes = [vp, u64, u64, u64, ctypes.c_int, vp, u32, vp, u32, ctypes.POINTER(u32), ctypes.POINTER(u32),
+                                 ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.nmsv_seam_scan.restype = ctypes.c_int
     sc = ctypes.POINTER(Scoring)
     L.nmsv_ssw_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, vp, u64, sc, ctypes.c_int, vp]
     L.nmsv_ssw_batch.restype = ctypes.c_int

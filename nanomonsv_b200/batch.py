@@ -80,6 +80,14 @@ class BatchBuilder:
                             _lib.MAPQ_NONE if mapq2 is None else int(mapq2)))
         return len(self._reads) - 1
 
+    def add_read_absent(self, length: int, mapq1: Optional[int], mapq2: Optional[int]) -> int:
+        """A read that is only counted (its mapq test fails, so it can never support): its sequence is not packed."""
+        assert self._open_sv is not None, "add_sv first"
+        idx = self.pack.add_absent(length)
+        self._reads.append((idx, self._open_sv, _lib.MAPQ_NONE if mapq1 is None else int(mapq1),
+                            _lib.MAPQ_NONE if mapq2 is None else int(mapq2)))
+        return len(self._reads) - 1
+
     def read_seq_index(self, read_row: int) -> int:
         return self._reads[read_row][0]
 

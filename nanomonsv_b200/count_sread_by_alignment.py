@@ -35,7 +35,7 @@ from .engine import DEFAULT_SCORING, AsciiSlice, Engine, SeqPack, default_engine
 from .my_seq import needs_explicit_revcomp, reverse_complement
 
 # maximum number of read bases packed into one device batch (host memory / H2D granularity, not a GPU limit)
-BATCH_BASES = int(os.environ.get("NMSV_BATCH_BASES", str(512 << 20)))
+BATCH_BASES = int(os.environ.get("NMSV_BATCH_BASES", str(160 << 20)))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -296,6 +296,21 @@ class SvJob:
     read_mapq: Dict[str, Tuple[Optional[int], Optional[int]]] = field(default_factory=dict)
     bases: int = 0
 
+    def read_id(self, ordinal: int) -> str:
+        return self.read_ids[ordinal]
+
+
+class _ScannedSv:
+    """Per-SV bookkeeping of a batch assembled from nmsv_seam_scan tables: what _drain needs to write the lines."""
+    __slots__ = ("key", "is_sbnd", "short", "data", "sreads", "first")
+
+    def __init__(self, key, is_sbnd, short, data, sreads, first):
+        self.key, self.is_sbnd, self.short, self.data, self.sreads, self.first = key, is_sbnd, short, data, sreads, first
+
+    def read_id(self, ordinal: int) -> str:
+        r = self.sreads[self.first + ordinal]
+        return self.data[int(r["id_off"]):int(r["id_off"]) + int(r["id_len"])].decode()
+
 
 def _mapq(v) -> Optional[int]:
     if v is None or v == "None":
@@ -334,7 +349,8 @@ class Alignment_counter(object):
         self._queued_bases = 0
         self.batches_run = 0
         self._pool: Optional[ThreadPoolExecutor] = None
-        self._pending = None            # (future, jobs, sv table) of the batch that is on the GPU
+        self._pending = []              # [(future, jobs, sv table)] of the batches that are on the GPU, oldest first
+        self._engines: List[Engine] = []
 
     # ---- reference-shaped interface
     def initialize(self, key, is_sbnd=False):
@@ -408,11 +424,17 @@ class Alignment_counter(object):
         bb = BatchBuilder(self.score_ratio_thres, self.start_pos_thres, self.end_pos_thres,
                           self.var_ref_margin_thres, self.var_read_min_mapq)
         shared: Dict[int, int] = {}      # id(sequence object) -> index in this batch's pack: the direct gather hands the
+        prune = getattr(eng, "prune", True)
+        q = self.var_read_min_mapq
         for job in self._queue:          # SAME str object to every SV candidate a read serves, so it is packed once
             bb.add_sv(job.templates, job.is_sbnd, job.short)
             for rid in job.read_ids:
                 m1, m2 = job.read_mapq.get(rid, (None, None))
                 seq = job.read_seqs[rid]
+                # a read whose mapq test fails is only counted (:344-346, :388-389): neither encoded nor uploaded
+                if prune and (m1 is None or m1 < q or (not job.is_sbnd and (m2 is None or m2 < q))):
+                    bb.add_read_absent(len(seq), m1, m2)
+                    continue
                 at = shared.get(id(seq)) if isinstance(seq, str) else None
                 if at is None:
                     r = bb.add_read(seq, m1, m2)
@@ -421,22 +443,119 @@ class Alignment_counter(object):
                 else:
                     bb.add_read_shared(at, m1, m2)
         pack, svs, reads = bb.finalize()
-        # The GPU call runs on a worker thread (ctypes releases the GIL), so the caller goes on parsing and encoding the
-        # next batch meanwhile; results are written strictly in submission order (at the next flush, or at close()).
-        if self._pool is None:
-            self._pool = ThreadPoolExecutor(max_workers=1)
-        fut = self._pool.submit(eng.validate, pack, svs, reads, self.scoring)
         queue, self._queue, self._queued_bases = self._queue, [], 0
-        self._drain()
-        self._pending = (fut, queue, svs)
+        self._launch(pack, svs, reads, queue)
+
+    def _launch(self, pack, svs, reads, metas):
+        """The GPU call runs on a worker thread (ctypes releases the GIL), so the caller goes on parsing and encoding the
+        next batch meanwhile; results are written strictly in submission order (at the next flush, or at close())."""
+        if self._pool is None:
+            # Two calls in flight: while the GPU finishes one batch (the end of a launch runs at low occupancy) the next
+            # one is uploaded and started. A context serves one call at a time, so the second call goes to a second
+            # context on the same GPU; it is created on first use and closed with the counter.
+            eng = self._engine or default_engine()
+            self._engines = [eng]
+            if isinstance(eng, Engine) and os.environ.get("NMSV_STAGE_INFLIGHT", "2") != "1":
+                self._engines.append(Engine(eng.device))
+                self._engines[1].set_option("prune", 1 if eng.prune else 0)
+            self._pool = ThreadPoolExecutor(max_workers=len(self._engines))
+        while len(self._pending) >= len(self._engines):
+            self._drain_one()
+        eng = self._engines[self.batches_run % len(self._engines)]
+        fut = self._pool.submit(eng.validate, pack, svs, reads, self.scoring)
+        self._pending.append((fut, metas, svs))
         self.batches_run += 1
 
+    def _submit_scanned(self, data, src, groups: np.ndarray, sreads: np.ndarray, is_sbnd: bool):
+        """A batch straight from the tables of nmsv_seam_scan: per SV candidate only the templates are built in Python
+        (reference :207-283); the read table is assembled with numpy, the sequences are encoded and packed by the
+        library from the mapping of the seam file, and reads whose mapq test already fails are neither encoded nor
+        uploaded (they are only counted, :344-346 / :388-389)."""
+        from .my_seq import encode
+        if self._queue:
+            self._submit()           # keep the output order when the class is also driven by hand
+        L = self.validate_sequence_length
+        ng, nr = len(groups), len(sreads)
+        svs = np.zeros(ng, dtype=_lib.SV_DTYPE)
+        svs["tmpl"] = _lib.NMSV_NONE
+        svs["tmpl_rc"] = _lib.NMSV_NONE
+        svs["read_begin"], svs["read_end"] = groups["read_begin"], groups["read_end"]
+        svs["margin"], svs["min_mapq"] = self.var_ref_margin_thres, self.var_read_min_mapq
+        tmpl_codes: List[np.ndarray] = []
+        metas = []
+        for g in range(ng):
+            ko, kl = int(groups["key_off"][g]), int(groups["key_len"][g])
+            key = data[ko:ko + kl].decode()
+            if is_sbnd:
+                var1, ref1 = sbnd_templates(key, self.reference_fasta_h, L)
+                templates, short = [var1, None, ref1, None], False
+            else:
+                var1, var2, ref1, ref2, short = canonical_templates(key, self.reference_fasta_h, L)
+                templates = [var1, var2, ref1 if short else None, ref2 if short else None]
+            seen: Dict[str, Tuple[int, int]] = {}
+            row = svs[g]
+            for slot, t in enumerate(templates):
+                if t is None:
+                    continue
+                if not t:
+                    raise ValueError("empty template")
+                if t not in seen:      # identical templates of one SV (var1 == var2 without an insertion) share work
+                    rc = _lib.NMSV_NONE
+                    if needs_explicit_revcomp(t):
+                        rc = len(tmpl_codes); tmpl_codes.append(encode(reverse_complement(t)))
+                    seen[t] = (len(tmpl_codes), rc)
+                    tmpl_codes.append(encode(t))
+                row["tmpl"][slot], row["tmpl_rc"][slot] = seen[t]
+            for v in (0, 1):
+                if templates[v] is not None:
+                    b = integer_bounds(len(templates[v]), self.score_ratio_thres, self.start_pos_thres, self.end_pos_thres)
+                    row["score_min"][v], row["qstart_max"][v], row["qend_min"][v] = b
+            row["flags"] = (_lib.SV_SBND if is_sbnd else 0) | (_lib.SV_SHORT_DEL_DUP if short else 0)
+            metas.append(_ScannedSv(key, is_sbnd, short, data, sreads, int(groups["read_begin"][g])))
+        # ---- sequence tables: templates first, then one entry per read
+        nt = len(tmpl_codes)
+        lens = np.empty(nt + nr, dtype=np.uint32)
+        lens[:nt] = [len(c) for c in tmpl_codes]
+        lens[nt:] = sreads["seq_len"]
+        m1, m2 = sreads["mapq1"], sreads["mapq2"]
+        keep = (m1 != _lib.MAPQ_NONE) & (m1 >= self.var_read_min_mapq)
+        if not is_sbnd:
+            keep &= (m2 != _lib.MAPQ_NONE) & (m2 >= self.var_read_min_mapq)
+        if not getattr(eng_prune_probe(self), "prune", True):
+            keep[:] = True
+        present = np.ones(nt + nr, dtype=bool)
+        present[nt:] = keep
+        padded = np.where(present, (lens.astype(np.uint64) + np.uint64(15)) & ~np.uint64(15), np.uint64(0))
+        offsets = np.zeros(nt + nr, dtype=np.uint64)
+        if nt + nr > 1:
+            np.cumsum(padded[:-1], out=offsets[1:])
+        total = int(offsets[-1] + padded[-1]) if nt + nr else 0
+        codes = np.empty(total, dtype=np.uint8)          # every byte is written below (sequences + their padding)
+        for i, c in enumerate(tmpl_codes):
+            o = int(offsets[i])
+            codes[o:o + len(c)] = c
+            codes[o + len(c):o + int(padded[i])] = 4
+        kidx = np.flatnonzero(keep)
+        if len(kidx):
+            so = np.ascontiguousarray(sreads["seq_off"][kidx])
+            ln = np.ascontiguousarray(sreads["seq_len"][kidx])
+            do = np.ascontiguousarray(offsets[nt + kidx])
+            _lib.load().nmsv_encode_pack_padded(src.ctypes.data, so.ctypes.data, ln.ctypes.data, do.ctypes.data, len(kidx),
+                                                codes.ctypes.data)
+        offsets[nt:][~keep] = _lib.SEQ_ABSENT
+        reads = np.zeros(nr, dtype=_lib.READ_DTYPE)
+        reads["seq"] = nt + np.arange(nr, dtype=np.uint32)
+        reads["sv"] = np.repeat(np.arange(ng, dtype=np.uint32), (groups["read_end"] - groups["read_begin"]).astype(np.int64))
+        reads["mapq1"], reads["mapq2"] = m1, (_lib.MAPQ_NONE if is_sbnd else m2)
+        self._launch(SeqPack.from_arrays(codes, offsets, lens), svs, reads, metas)
+
     def _drain(self):
-        """Wait for the batch in flight (if any) and write its count / info lines."""
-        if self._pending is None:
-            return
-        fut, queue, svs = self._pending
-        self._pending = None
+        """Wait for the batches in flight and write their count / info lines, in submission order."""
+        while self._pending:
+            self._drain_one()
+
+    def _drain_one(self):
+        fut, queue, svs = self._pending.pop(0)
         checked, supporting, records = fut.result()       # re-raises an EngineError of the worker
         by_sv: Dict[int, list] = {}
         for rec in records:
@@ -445,7 +564,7 @@ class Alignment_counter(object):
             head = "\t".join(job.key.split(","))
             print(f"{head}\t{int(checked[i])}\t{int(supporting[i])}", file=self.hout_count)
             for rec in by_sv.get(i, []):
-                rid = job.read_ids[int(rec["read"]) - int(svs[i]["read_begin"])]
+                rid = job.read_id(int(rec["read"]) - int(svs[i]["read_begin"]))
                 if job.is_sbnd:
                     fields = _aln_list(rec["aln"][0])
                 else:
@@ -458,6 +577,9 @@ class Alignment_counter(object):
         if self._pool is not None:
             self._pool.shutdown(wait=True)
             self._pool = None
+            for extra in self._engines[1:]:
+                extra.close()
+            self._engines = []
         for h in (self.hout_count, self.hout_ainfo):
             if not h.closed:
                 h.close()
@@ -476,7 +598,7 @@ class Alignment_counter(object):
         self.close()
 
     def __del__(self):
-        unfinished = bool(getattr(self, "_queue", None)) or getattr(self, "_pending", None) is not None
+        unfinished = bool(getattr(self, "_queue", None)) or bool(getattr(self, "_pending", None))
         try:
             self.close()
         except Exception as exc:      # an error of the GPU batch must not vanish with the object
@@ -490,7 +612,48 @@ class Alignment_counter(object):
                               "garbage collection", RuntimeWarning)
 
 
+def eng_prune_probe(counter) -> Engine:
+    return counter._engine or default_engine()
+
+
 _WS = b" \t\r\n\x0b\x0c"
+
+
+def _stream_seam_native(seam_file: str, counter: Alignment_counter, is_sbnd: bool) -> None:
+    """The group-by of the reference's loop (:414-425 / :436-448) done by the library in one pass over a mapping of the
+    seam file (nmsv_seam_scan): Python sees one table of key groups and one of reads per device batch, builds the
+    templates of each candidate, and hands the batch to the GPU while the next one is scanned. The line-by-line reader
+    (NMSV_SEAM_READER=lines) stays the executable specification; tests hold the readers to identical outputs."""
+    import ctypes
+    import mmap
+    L = _lib.load()
+    with open(seam_file, "rb") as hin:
+        size = os.fstat(hin.fileno()).st_size
+        if size:
+            data = mmap.mmap(hin.fileno(), 0, access=mmap.ACCESS_READ)
+            src = np.frombuffer(data, dtype=np.uint8)
+            gcap, rcap = 4096, 1 << 17
+            groups = np.zeros(gcap, dtype=_lib.SEAM_GROUP_DTYPE)
+            sreads = np.zeros(rcap, dtype=_lib.SEAM_READ_DTYPE)
+            ng, nr = ctypes.c_uint32(0), ctypes.c_uint32(0)
+            nxt, err = ctypes.c_uint64(0), ctypes.c_uint64(0)
+            pos = 0
+            while pos < size:
+                rc = L.nmsv_seam_scan(src.ctypes.data, size, pos, BATCH_BASES, 1 if is_sbnd else 0, groups.ctypes.data,
+                                      gcap, sreads.ctypes.data, rcap, ctypes.byref(ng), ctypes.byref(nr),
+                                      ctypes.byref(nxt), ctypes.byref(err))
+                if rc == _lib.E_CAPACITY:          # one candidate with more reads than the table holds
+                    rcap *= 2
+                    sreads = np.zeros(rcap, dtype=_lib.SEAM_READ_DTYPE)
+                    continue
+                if rc != 0:
+                    line_no = data[:err.value].count(b"\n") + 1
+                    raise ValueError(f"{seam_file}: line {line_no} is not `key, read id, mapq1, mapq2, sequence` (5 tab-separated "
+                                     "fields, integer or None mapping qualities)")
+                if ng.value:
+                    counter._submit_scanned(data, src, groups[:ng.value].copy(), sreads[:nr.value].copy(), is_sbnd)
+                pos = nxt.value
+    counter.close()          # waits for the batches in flight: their tables keep the mapping alive until then
 
 
 def _stream_seam_fast(seam_file: str, counter: Alignment_counter, is_sbnd: bool) -> None:
@@ -562,8 +725,10 @@ def count_sread_from_seam(seam_file, output_count_file, output_alignment_info_fi
     """The part of count_sread_by_alignment after read gathering: seam TSV -> sread_count / sread_info files."""
     counter = Alignment_counter(output_count_file, output_alignment_info_file, reference_fasta, var_read_min_mapq,
                                 score_ratio_thres, False, debug, engine=engine, **kwargs)
-    # NMSV_SEAM_READER=lines selects the line-by-line reader that mirrors the reference's loop
-    reader = _stream_seam if os.environ.get("NMSV_SEAM_READER", "bytes") == "lines" else _stream_seam_fast
+    # NMSV_SEAM_READER=lines selects the line-by-line reader that mirrors the reference's loop, =bytes the Python
+    # byte-level reader of round 1; the default is the library's one-pass scan
+    reader = {"lines": _stream_seam, "bytes": _stream_seam_fast}.get(os.environ.get("NMSV_SEAM_READER", "native"),
+                                                                     _stream_seam_native)
     reader(seam_file, counter, is_sbnd)
     return counter
 

@@ -18,6 +18,9 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "../../include/nmsv.h"
 #include "nmsv_sw.cuh"
@@ -40,7 +43,11 @@ static int choose_class(uint32_t len)
     // Cheapest strip height for a template of `len` rows. One warp-step of the kernel costs about 8.25 * R issue cycles
     // of DPX work (66 DPX per 16 rows, 2 cycles each) plus ~34 cycles that do not depend on R (shuffles, profile and
     // ring loads, floor chain, loop), and a task runs tiles(len, R) * (columns + 31) steps: padded rows are paid for,
-    // but so are short strips. Ties -> taller strips (fewer boundary round trips).
+    // but so are short strips. The tiles of a task run side by side on the 4 warps of a block: beyond 4 tiles a task
+    // is dealt out in groups of 4 (every fourth boundary row goes through a whole-read buffer), so a tile count that is
+    // not a multiple of 4 leaves part of a group to other tasks' phase, and strips taller than 16 rows run at 12
+    // instead of 16 warps per SM -- measured on 6000-row templates: R = 16 (12 tiles) 6.54 TCUPS, R = 19 (10 tiles)
+    // 5.77, R = 13 (15 tiles) 5.85. Ties -> taller strips.
     static const int forced = [] { const char* e = getenv("NMSV_FORCE_R"); return e ? atoi(e) : 0; }();   // measurement knob
     if (forced)
         for (int c = 0; c < kNumClasses; ++c) if (kClassR[c] == forced) return c;
@@ -48,7 +55,9 @@ static int choose_class(uint32_t len)
     double best_cost = 0.0;
     for (int c = 0; c < kNumClasses; ++c) {
         const uint64_t tile = 32ull * kClassR[c];
-        const double cost = (double)((len + tile - 1) / tile) * (8.25 * kClassR[c] + 34.0);
+        uint64_t tiles = (len + tile - 1) / tile;
+        if (tiles > (uint64_t)kW) tiles = (tiles + kW - 1) / kW * kW;
+        const double cost = (double)tiles * (8.25 * kClassR[c] + 34.0) * (kClassR[c] > 16 ? 1.10 : 1.0);
         if (best < 0 || cost <= best_cost) { best_cost = cost; best = c; }
     }
     return best;
@@ -290,31 +299,203 @@ static const uint8_t* code_table()
 // Host-side packing for callers that hold the reads as ASCII inside one large buffer (a seam TSV read or mapped in
 // blocks): sequence i = src[src_off[i] .. +lens[i]) is encoded straight to dst[dst_off[i] ..), one pass, no
 // intermediate copies. Bytes of dst between the sequences are left as they are (the caller pre-fills the padding).
+static void encode_scalar(const uint8_t* in, uint8_t* out, uint64_t n)
+{
+    const uint8_t* tab = code_table();
+    for (uint64_t i = 0; i < n; ++i) out[i] = tab[in[i]];
+}
+
+#if defined(__x86_64__)
+// 32 bases per step: fold case (c | 0x20), four byte compares, code = 4 - 4*[a] - 3*[c] - 2*[g] - 1*[t]
+__attribute__((target("avx2"))) static void encode_avx2(const uint8_t* in, uint8_t* out, uint64_t n)
+{
+    const __m256i lower = _mm256_set1_epi8(0x20), four = _mm256_set1_epi8(4);
+    const __m256i ca = _mm256_set1_epi8('a'), cc = _mm256_set1_epi8('c'), cg = _mm256_set1_epi8('g'), ct = _mm256_set1_epi8('t');
+    const __m256i k4 = _mm256_set1_epi8(4), k3 = _mm256_set1_epi8(3), k2 = _mm256_set1_epi8(2), k1 = _mm256_set1_epi8(1);
+    uint64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i v = _mm256_or_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i)), lower);
+        __m256i r = four;
+        r = _mm256_sub_epi8(r, _mm256_and_si256(_mm256_cmpeq_epi8(v, ca), k4));
+        r = _mm256_sub_epi8(r, _mm256_and_si256(_mm256_cmpeq_epi8(v, cc), k3));
+        r = _mm256_sub_epi8(r, _mm256_and_si256(_mm256_cmpeq_epi8(v, cg), k2));
+        r = _mm256_sub_epi8(r, _mm256_and_si256(_mm256_cmpeq_epi8(v, ct), k1));
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + i), r);
+    }
+    encode_scalar(in + i, out + i, n - i);
+}
+#endif
+
+// (c | 0x20) also folds a few non-letters onto a/c/g/t: 'A'^0x20 pairs only -- 0x41/0x61, 0x43/0x63, 0x47/0x67, 0x54/0x74
+// are the ONLY bytes whose (c | 0x20) equals a, c, g or t, so the vector path equals the table.
+static void encode_bytes(const uint8_t* in, uint8_t* out, uint64_t n)
+{
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { encode_avx2(in, out, n); return; }
+#endif
+    encode_scalar(in, out, n);
+}
+
 extern "C" void nmsv_encode_pack(const char* src, const uint64_t* src_off, const uint32_t* lens, const uint64_t* dst_off,
                                  uint64_t n_seqs, uint8_t* dst)
 {
-    const uint8_t* tab = code_table();
+    for (uint64_t s = 0; s < n_seqs; ++s)
+        encode_bytes(reinterpret_cast<const uint8_t*>(src) + src_off[s], dst + dst_off[s], lens[s]);
+}
+
+// the same, and every sequence is padded with the wildcard code up to the next 16-byte boundary (dst_off[] must be
+// 16-byte aligned): the destination buffer needs no pre-fill
+extern "C" void nmsv_encode_pack_padded(const char* src, const uint64_t* src_off, const uint32_t* lens,
+                                        const uint64_t* dst_off, uint64_t n_seqs, uint8_t* dst)
+{
     for (uint64_t s = 0; s < n_seqs; ++s) {
-        const uint8_t* in = reinterpret_cast<const uint8_t*>(src) + src_off[s];
         uint8_t* out = dst + dst_off[s];
-        const uint32_t n = lens[s];
-        for (uint32_t i = 0; i < n; ++i) out[i] = tab[in[i]];
+        const uint64_t n = lens[s];
+        encode_bytes(reinterpret_cast<const uint8_t*>(src) + src_off[s], out, n);
+        for (uint64_t i = n; i < ((n + 15) & ~15ull); ++i) out[i] = 4;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side of the stage seam: the group-by over the key-sorted seam TSV (count_sread_by_alignment.py:414-448)
+// ------------------------------------------------------------------------------------------------------------------
+static inline bool seam_ws(unsigned char c)      // bytes.strip() of the sequence / str.split() of the read id
+{
+    return c == ' ' || (c >= '\t' && c <= '\r') || (c >= 0x1c && c <= 0x1f);
+}
+
+static bool seam_mapq(const char* p, const char* e, int32_t* out)
+{
+    if (e - p == 4 && !memcmp(p, "None", 4)) { *out = NMSV_MAPQ_NONE; return true; }
+    while (p < e && seam_ws((unsigned char)*p)) ++p;
+    while (e > p && seam_ws((unsigned char)e[-1])) --e;
+    bool neg = false;
+    if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+    if (p == e) return false;
+    long long v = 0;
+    for (; p < e; ++p) {
+        if (*p < '0' || *p > '9') return false;
+        v = v * 10 + (*p - '0');
+        if (v > 0x7fffffffLL) return false;
+    }
+    *out = (int32_t)(neg ? -v : v);
+    return true;
+}
+
+extern "C" int nmsv_seam_scan(const char* data, uint64_t size, uint64_t start, uint64_t max_bases, int is_sbnd,
+                              nmsv_seam_group* groups, uint32_t group_cap, nmsv_seam_read* reads, uint32_t read_cap,
+                              uint32_t* n_groups, uint32_t* n_reads, uint64_t* next, uint64_t* error_off)
+{
+    if (!data || !groups || !reads || !n_groups || !n_reads || !next) return NMSV_E_INVALID;
+    uint32_t ng = 0, nr = 0;
+    uint64_t bases = 0, pos = start;
+    std::vector<int32_t> table;          // open addressing over the reads of the current group: index into reads, -1 = free
+    auto id_hash = [&](const char* p, uint32_t n) {
+        uint64_t h = 1469598103934665603ull;
+        for (uint32_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 1099511628211ull; }
+        return h;
+    };
+    auto rebuild = [&](uint32_t begin, uint32_t end, size_t cap) {
+        table.assign(cap, -1);
+        for (uint32_t r = begin; r < end; ++r) {
+            size_t at = id_hash(data + reads[r].id_off, reads[r].id_len) & (cap - 1);
+            while (table[at] >= 0) at = (at + 1) & (cap - 1);
+            table[at] = (int32_t)r;
+        }
+    };
+    *n_groups = 0; *n_reads = 0; *next = start;
+    while (pos < size) {
+        // ---- one key group
+        const uint64_t group_start = pos;
+        const uint32_t first_read = nr;
+        const char* key = nullptr;
+        uint32_t key_len = 0;
+        uint64_t group_bases = 0;
+        size_t cap = 64;
+        table.assign(cap, -1);
+        bool overflow = false;
+        while (pos < size) {
+            const char* line = data + pos;
+            const char* le = (const char*)memchr(line, '\n', size - pos);
+            if (!le) le = data + size;
+            const char* t[4];
+            const char* q = line;
+            int nt = 0;
+            while (nt < 4) {
+                const char* tab = (const char*)memchr(q, '\t', le - q);
+                if (!tab) break;
+                t[nt++] = tab; q = tab + 1;
+            }
+            if (nt < 4 || memchr(q, '\t', le - q)) { if (error_off) *error_off = pos; return NMSV_E_INVALID; }
+            const uint32_t klen = (uint32_t)(t[0] - line);
+            if (!key) { key = line; key_len = klen; }
+            else if (klen != key_len || memcmp(key, line, klen)) break;        // next group starts here
+            // read id: first whitespace-separated token of the second field (the FASTA header round trip, pyssw.py:41)
+            const char* ib = t[0] + 1;
+            const char* ie = t[1];
+            while (ib < ie && seam_ws((unsigned char)*ib)) ++ib;
+            const char* ix = ib;
+            while (ix < ie && !seam_ws((unsigned char)*ix)) ++ix;
+            int32_t m1, m2 = NMSV_MAPQ_NONE;
+            if (!seam_mapq(t[1] + 1, t[2], &m1) || (!is_sbnd && !seam_mapq(t[2] + 1, t[3], &m2))) {
+                if (error_off) *error_off = pos;
+                return NMSV_E_INVALID;
+            }
+            const char* sb = t[3] + 1;
+            const char* se = le;
+            while (se > sb && seam_ws((unsigned char)se[-1])) --se;
+            while (sb < se && seam_ws((unsigned char)*sb)) ++sb;
+            // the dict of the reference (:162, add_long_read_seq): the last record of an id gives its mapq; its sequence is
+            // the last non-empty one; ids are ordered by their first non-empty record
+            const uint32_t idl = (uint32_t)(ix - ib);
+            size_t at = id_hash(ib, idl) & (cap - 1);
+            int32_t hit = -1;
+            while (table[at] >= 0) {
+                const nmsv_seam_read& o = reads[table[at]];
+                if (o.id_len == idl && !memcmp(data + o.id_off, ib, idl)) { hit = table[at]; break; }
+                at = (at + 1) & (cap - 1);
+            }
+            if (hit >= 0) {
+                nmsv_seam_read& o = reads[hit];
+                o.mapq1 = m1; o.mapq2 = m2;
+                if (se > sb) {
+                    group_bases += (uint64_t)(se - sb); group_bases -= o.seq_len;
+                    o.seq_off = (uint64_t)(sb - data); o.seq_len = (uint32_t)(se - sb);
+                }
+            } else if (se > sb) {
+                if (nr >= read_cap) { overflow = true; break; }
+                nmsv_seam_read& o = reads[nr];
+                o.id_off = (uint64_t)(ib - data); o.id_len = idl;
+                o.seq_off = (uint64_t)(sb - data); o.seq_len = (uint32_t)(se - sb);
+                o.mapq1 = m1; o.mapq2 = m2;
+                table[at] = (int32_t)nr;
+                ++nr;
+                group_bases += o.seq_len;
+                if ((size_t)(nr - first_read) * 2 > cap) { cap *= 2; rebuild(first_read, nr, cap); }
+            }
+            pos = (uint64_t)(le - data) + 1;
+        }
+        if (overflow || ng >= group_cap) {       // this group does not fit: it belongs to the next call
+            if (ng == 0) return NMSV_E_CAPACITY;
+            nr = first_read;
+            pos = group_start;
+            break;
+        }
+        nmsv_seam_group& g = groups[ng++];
+        g.key_off = (uint64_t)(key - data); g.key_len = key_len;
+        g.read_begin = first_read; g.read_end = nr; g.reserved = 0;
+        bases += group_bases;
+        if (pos > size) pos = size;
+        if (bases >= max_bases) break;
+    }
+    *n_groups = ng; *n_reads = nr; *next = pos > size ? size : pos;
+    return NMSV_OK;
 }
 
 extern "C" void nmsv_encode_ascii(const char* ascii, uint64_t n, uint8_t* codes)
 {
-    for (uint64_t i = 0; i < n; ++i) {
-        uint8_t c;
-        switch (ascii[i]) {
-        case 'A': case 'a': c = 0; break;
-        case 'C': case 'c': c = 1; break;
-        case 'G': case 'g': c = 2; break;
-        case 'T': case 't': c = 3; break;
-        default: c = 4;
-        }
-        codes[i] = c;
-    }
+    encode_bytes(reinterpret_cast<const uint8_t*>(ascii), codes, n);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -810,16 +991,17 @@ static int check_seq_tables(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_code
 {
     if (!codes || !offsets || !lens) return set_err(ctx, NMSV_E_INVALID, "codes/offsets/lens must not be NULL");
     for (uint32_t s = 0; s < n_seqs; ++s)
-        if (offsets[s] > n_codes || (uint64_t)lens[s] > n_codes - offsets[s])
+        if (offsets[s] != NMSV_SEQ_ABSENT && (offsets[s] > n_codes || (uint64_t)lens[s] > n_codes - offsets[s]))
             return set_err(ctx, NMSV_E_INVALID, "sequence %u (offset %llu, len %u) lies outside the %llu-byte code buffer",
                            s, (unsigned long long)offsets[s], lens[s], (unsigned long long)n_codes);
     return NMSV_OK;
 }
 
-static int check_template(nmsv_ctx* ctx, uint32_t idx, const uint32_t* lens, uint32_t n_seqs, const nmsv_scoring* sc, const char* what)
+static int check_template(nmsv_ctx* ctx, uint32_t idx, const uint64_t* offsets, const uint32_t* lens, uint32_t n_seqs, const nmsv_scoring* sc, const char* what)
 {
     if (idx >= n_seqs) return set_err(ctx, NMSV_E_INVALID, "%s index %u out of range (n_seqs %u)", what, idx, n_seqs);
     if (lens[idx] == 0) return set_err(ctx, NMSV_E_INVALID, "%s %u is empty", what, idx);
+    if (offsets[idx] == NMSV_SEQ_ABSENT) return set_err(ctx, NMSV_E_INVALID, "%s %u has no sequence (NMSV_SEQ_ABSENT)", what, idx);
     // No limit on the length: parasail returns NULL only when a score actually leaves the 16-bit range, and so does the
     // kernel (a task whose bound match * min(rows, columns) exceeds sw_score_cap is watched at run time, nmsv_sw.cuh).
     (void)sc;
@@ -948,10 +1130,10 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
         pl->checked[i] = (int32_t)(sv.read_end - sv.read_begin);
         for (int s = 0; s < 4; ++s) {
             if (sv.tmpl[s] == NMSV_NONE) continue;
-            rc = check_template(ctx, sv.tmpl[s], lens, n_seqs, scoring, "template");
+            rc = check_template(ctx, sv.tmpl[s], offsets, lens, n_seqs, scoring, "template");
             if (rc) return rc;
             if (sv.tmpl_rc[s] != NMSV_NONE) {
-                rc = check_template(ctx, sv.tmpl_rc[s], lens, n_seqs, scoring, "reverse-complement template");
+                rc = check_template(ctx, sv.tmpl_rc[s], offsets, lens, n_seqs, scoring, "reverse-complement template");
                 if (rc) return rc;
                 if (lens[sv.tmpl_rc[s]] != lens[sv.tmpl[s]])
                     return set_err(ctx, NMSV_E_INVALID, "SV %u slot %d: explicit reverse complement has a different length", i, s);
@@ -993,6 +1175,8 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
                              : (rd.mapq1 != NMSV_MAPQ_NONE && rd.mapq1 >= sv.min_mapq && rd.mapq2 != NMSV_MAPQ_NONE && rd.mapq2 >= sv.min_mapq);
         const bool pruned = pl->prune && !mq;
         if (pruned) stt.reads_pruned += 1;
+        else if (offsets[rd.seq] == NMSV_SEQ_ABSENT)
+            return set_err(ctx, NMSV_E_INVALID, "read %u must be aligned but its sequence %u was not supplied (NMSV_SEQ_ABSENT)", r, rd.seq);
         uint64_t c = 0;
         bool spawner = false;
         for (int s = 0; s < 4; ++s) {
@@ -1356,14 +1540,15 @@ static int run_pairs(nmsv_ctx* ctx, const uint8_t* codes, uint64_t n_codes, cons
     bool class_used[8] = {false};
     uint32_t max_cols_multi = 0;
     for (uint32_t i = 0; i < n_pairs; ++i) {
-        rc = check_template(ctx, tmpl_idx[i], lens, n_seqs, sc, "template");
+        rc = check_template(ctx, tmpl_idx[i], offsets, lens, n_seqs, sc, "template");
         if (rc) return rc;
         if (rc_idx && rc_idx[i] != NMSV_NONE) {
-            rc = check_template(ctx, rc_idx[i], lens, n_seqs, sc, "reverse-complement template");
+            rc = check_template(ctx, rc_idx[i], offsets, lens, n_seqs, sc, "reverse-complement template");
             if (rc) return rc;
             if (lens[rc_idx[i]] != lens[tmpl_idx[i]]) return set_err(ctx, NMSV_E_INVALID, "pair %u: explicit reverse complement has a different length", i);
         }
-        if (read_idx[i] >= n_seqs || lens[read_idx[i]] == 0) return set_err(ctx, NMSV_E_INVALID, "pair %u: read index %u invalid or empty", i, read_idx[i]);
+        if (read_idx[i] >= n_seqs || lens[read_idx[i]] == 0 || offsets[read_idx[i]] == NMSV_SEQ_ABSENT)
+            return set_err(ctx, NMSV_E_INVALID, "pair %u: read index %u invalid or empty", i, read_idx[i]);
         const int c = choose_class(lens[tmpl_idx[i]]);
         st.cls_host[tmpl_idx[i]] = (uint8_t)kClassR[c];
         class_used[c] = true;

@@ -5,6 +5,7 @@ Nothing here computes alignments; every method ends in a call into libnmsv_sw.so
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from dataclasses import dataclass
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
@@ -71,6 +72,14 @@ class SeqPack:
         self._lens.append(piece.length)
         return len(self._lens) - 1
 
+    def add_absent(self, length: int) -> int:
+        """A sequence of which only the length is supplied (offset NMSV_SEQ_ABSENT): the sequence of a read that is only
+        counted because its mapq test already fails."""
+        assert self._frozen is None, "SeqPack already finalized"
+        self._chunks.append(None)
+        self._lens.append(int(length))
+        return len(self._lens) - 1
+
     def add_codes(self, codes: np.ndarray) -> int:
         assert self._frozen is None, "SeqPack already finalized"
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
@@ -89,7 +98,8 @@ class SeqPack:
             # every sequence starts on a 16-byte boundary (filled with the wildcard code): the kernel stages reads
             # with 16-byte-granular bulk copies (TMA); unaligned offsets are legal but take the plain-load path
             lens = np.asarray(self._lens, dtype=np.uint32)
-            padded = (lens.astype(np.uint64) + np.uint64(15)) & ~np.uint64(15)
+            absent = np.fromiter((c is None for c in self._chunks), dtype=bool, count=len(self._chunks))
+            padded = np.where(absent, np.uint64(0), (lens.astype(np.uint64) + np.uint64(15)) & ~np.uint64(15))
             offsets = np.zeros(len(lens), dtype=np.uint64)
             if len(lens) > 1:
                 np.cumsum(padded[:-1], out=offsets[1:])
@@ -97,6 +107,8 @@ class SeqPack:
             codes = np.full(total, 4, dtype=np.uint8)
             lazy: Dict[int, list] = {}          # id(source block) -> [(source, start, length, destination offset)]
             for off, chunk in zip(offsets.tolist(), self._chunks):
+                if chunk is None:
+                    continue
                 if isinstance(chunk, AsciiSlice):
                     lazy.setdefault(id(chunk.src), []).append((chunk.src, chunk.start, chunk.length, off))
                 else:
@@ -108,6 +120,7 @@ class SeqPack:
                 do = np.array([i[3] for i in items], dtype=np.uint64)
                 _lib.load().nmsv_encode_pack(src.ctypes.data, so.ctypes.data, ln.ctypes.data, do.ctypes.data, len(items),
                                              codes.ctypes.data)
+            offsets[absent] = _lib.SEQ_ABSENT
             self._frozen = (codes, offsets, lens)
             self._chunks = []
         return self._frozen
@@ -197,6 +210,7 @@ class Engine:
         self._h = h
         self.device = int(device)
         self._plans = weakref.WeakSet()      # live plans: destroyed before the context (they use its stream and pool)
+        self.prune = os.environ.get("NMSV_PRUNE", "1") != "0"      # mirrors the context's "prune" option
 
     # ---- plumbing
     def _check(self, rc: int) -> None:
@@ -213,6 +227,8 @@ class Engine:
     def set_option(self, name: str, value: int) -> None:
         """nmsv_set_option: "prune" = 0 computes every alignment the reference runs (parity tests)."""
         self._check(self._L.nmsv_set_option(self._h, name.encode(), int(value)))
+        if name == "prune":
+            self.prune = bool(value)
 
     def __enter__(self):
         return self

@@ -196,14 +196,41 @@ def test_byte_level_seam_reader_builds_the_same_batches(tmp_path, monkeypatch, s
         for a, b in zip(ref_batches, batches):
             for x, y in zip(a, b):
                 assert x.dtype == y.dtype and x.shape == y.shape and (x == y).all(), key
+    # the library's one-pass scan (nmsv_seam_scan, the default reader) lays a batch out differently (templates first, one
+    # table per batch, mapq-failing reads as lengths only): same candidates, templates, reads in the same order, counts
+    def canonical(batches):
+        res = []
+        for codes, offsets, lens, svs, reads in batches:
+            def seq(i):
+                if int(offsets[i]) == _lib.SEQ_ABSENT:
+                    return ("absent", int(lens[i]))
+                return bytes(codes[int(offsets[i]):int(offsets[i]) + int(lens[i])])
+            for sv in svs:
+                tm = tuple(seq(int(t)) if int(t) != _lib.NMSV_NONE else None for t in sv["tmpl"])
+                rc = tuple(seq(int(t)) if int(t) != _lib.NMSV_NONE else None for t in sv["tmpl_rc"])
+                rs = [(int(r["mapq1"]), int(r["mapq2"]), seq(int(r["seq"]))) for r in reads[int(sv["read_begin"]):int(sv["read_end"])]]
+                res.append((tm, rc, rs, tuple(int(x) for x in sv["score_min"]), tuple(int(x) for x in sv["qstart_max"]),
+                            tuple(int(x) for x in sv["qend_min"]), int(sv["margin"]), int(sv["min_mapq"]), int(sv["flags"])))
+        return res
+    for batch_bases in (512 << 20, 20000):
+        monkeypatch.setenv("NMSV_SEAM_READER", "native")
+        monkeypatch.setattr(C, "BATCH_BASES", batch_bases)
+        eng = _RecordingEngine()
+        fc, fi = str(tmp_path / f"native{batch_bases}.count"), str(tmp_path / f"native{batch_bases}.info")
+        C.count_sread_from_seam(seam, fc, fi, wl.fasta, sbnd, 40, 1.2, engine=eng)
+        ref_batches, ref_count = out[("lines", batch_bases)]
+        assert open(fc).read() == ref_count and len(eng.batches) == len(ref_batches)
+        assert canonical(eng.batches) == canonical(ref_batches)
+        assert any(int(o) == _lib.SEQ_ABSENT for b in eng.batches for o in b[1])
     # the extra lines did what they are there for
     codes, offsets, lens, svs, reads = out[("lines", 512 << 20)][0][0]
     n_first = int(svs["read_end"][0]) - int(svs["read_begin"][0])
     assert n_first == sum(1 for ln in lines if ln.split("\t")[0] == k0) + 2   # dup_read once, empty_read dropped
-    with pytest.raises(ValueError):
-        open(seam, "a").write("\nbroken line without tabs\n")
-        monkeypatch.setenv("NMSV_SEAM_READER", "bytes")
-        C.count_sread_from_seam(seam, fc, fi, wl.fasta, sbnd, 40, 1.2, engine=_RecordingEngine())
+    open(seam, "a").write("\nbroken line without tabs\n")
+    for reader in ("bytes", "native"):
+        monkeypatch.setenv("NMSV_SEAM_READER", reader)
+        with pytest.raises(ValueError):
+            C.count_sread_from_seam(seam, fc, fi, wl.fasta, sbnd, 40, 1.2, engine=_RecordingEngine())
 
 
 def test_device_pick_follows_env_then_pool_worker(monkeypatch):

@@ -124,7 +124,9 @@ def _per_sv_reads(batches):
     """[(templates as code bytes, {(mapq1, mapq2, read as code bytes)})] over all batches, in SV order."""
     out = []
     for codes, offsets, lens, svs, reads in batches:
-        def seq(i):
+        def seq(i):      # a read that is only counted (mapq test fails) travels as a length without a sequence
+            if int(offsets[i]) == 0xFFFFFFFFFFFFFFFF:
+                return ("absent", int(lens[i]))
             return bytes(codes[int(offsets[i]):int(offsets[i]) + int(lens[i])])
         for sv in svs:
             tm = tuple(seq(int(t)) if int(t) != 0xffffffff else None for t in sv["tmpl"])
