@@ -268,6 +268,17 @@ def stage_seam_e2e(eng, wl, order, n_cand, checked, supporting, n_records) -> di
             return time.perf_counter() - t0
         run()                       # warm-up (page cache, pools)
         dt = min(run(), run())
+        sweep = {}
+        if os.environ.get("NMSV_BENCH_STAGE_SWEEP"):      # batch-size sweep (measurement knob)
+            default = C.BATCH_BASES
+            for fl in (2, 3, 4):
+                for mb in (16, 32, 64):
+                    C.BATCH_BASES, C.INFLIGHT = mb << 20, fl
+                    run()
+                    sweep[f"{mb}MB x{fl}"] = n_cand / min(run(), run())
+            C.INFLIGHT = 3
+            C.BATCH_BASES = default
+            log("[stage seam] candidates/s by batch size:", {k: round(v) for k, v in sweep.items()})
         got_c, got_s, n_info = [], [], 0
         for sample in ("tumor", "control"):
             for line in open(seams[sample] + ".count"):

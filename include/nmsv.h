@@ -187,8 +187,9 @@ void nmsv_encode_pack_padded(const char *src, const uint64_t *src_off, const uin
  * (a mapping of the file): consecutive lines with the same key form a group (one SV candidate); inside a group the
  * reference's dict semantics are applied (read id = first blank-separated token, pyssw.py:41; the last record of an id
  * gives its mapq, its sequence is the last non-empty one, an id without any sequence is dropped; "None" = NMSV_MAPQ_NONE;
- * is_sbnd: mapq2 is None). Whole groups are consumed from `start` until at least max_bases read bases are collected or a
- * buffer is full; *next is where the next call starts. All offsets point into `data`: the caller encodes the sequences
+ * is_sbnd: mapq2 is None). Whole groups are consumed from `start` until at least max_bases read bases are collected (and
+ * at least tail_bytes of the file remain: a short rest is not left for a batch of its own) or a buffer is full; *next
+ * is where the next call starts. All offsets point into `data`: the caller encodes the sequences
  * straight from there with nmsv_encode_pack. Host only, no ctx. NMSV_E_INVALID: malformed line at *error_off;
  * NMSV_E_CAPACITY: the first group alone does not fit the buffers. */
 typedef struct {
@@ -208,7 +209,7 @@ typedef struct {
     int32_t mapq2;
 } nmsv_seam_read;
 
-int nmsv_seam_scan(const char *data, uint64_t size, uint64_t start, uint64_t max_bases, int is_sbnd,
+int nmsv_seam_scan(const char *data, uint64_t size, uint64_t start, uint64_t max_bases, uint64_t tail_bytes, int is_sbnd,
                    nmsv_seam_group *groups, uint32_t group_cap, nmsv_seam_read *reads, uint32_t read_cap,
                    uint32_t *n_groups, uint32_t *n_reads, uint64_t *next, uint64_t *error_off);
 

@@ -128,7 +128,7 @@ def load() -> ctypes.CDLL:
     L.nmsv_encode_pack.restype = None
     L.nmsv_encode_pack_padded.argtypes = [vp, vp, vp, vp, u64, vp]
     L.nmsv_encode_pack_padded.restype = None
-    L.nmsv_seam_scan.argtypes = [vp, u64, u64, u64, ctypes.c_int, vp, u32, vp, u32, ctypes.POINTER(u32), ctypes.POINTER(u32),
+    L.nmsv_seam_scan.argtypes = [vp, u64, u64, u64, u64, ctypes.c_int, vp, u32, vp, u32, ctypes.POINTER(u32), ctypes.POINTER(u32),
                                  ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.nmsv_seam_scan.restype = ctypes.c_int
     sc = ctypes.POINTER(Scoring)

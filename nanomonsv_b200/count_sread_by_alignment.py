@@ -35,7 +35,13 @@ from .engine import DEFAULT_SCORING, AsciiSlice, Engine, SeqPack, default_engine
 from .my_seq import needs_explicit_revcomp, reverse_complement
 
 # maximum number of read bases packed into one device batch (host memory / H2D granularity, not a GPU limit)
-BATCH_BASES = int(os.environ.get("NMSV_BATCH_BASES", str(160 << 20)))
+# Measured on the bench's seam files (one Python process, one B200, candidates/s through count_sread_from_seam):
+# 8 MB 615, 16 MB 941, 32 MB 1034, 64 MB 818, 160 MB 821 -- small enough that parsing batch k+1 hides behind the GPU
+# work of batch k, large enough that a launch is not all tail.
+BATCH_BASES = int(os.environ.get("NMSV_BATCH_BASES", str(32 << 20)))
+# GPU calls in flight per Alignment_counter (each on a context of its own): the end of a launch runs at low occupancy,
+# the next calls fill it
+INFLIGHT = int(os.environ.get("NMSV_STAGE_INFLIGHT", "3"))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -455,13 +461,28 @@ class Alignment_counter(object):
             # context on the same GPU; it is created on first use and closed with the counter.
             eng = self._engine or default_engine()
             self._engines = [eng]
-            if isinstance(eng, Engine) and os.environ.get("NMSV_STAGE_INFLIGHT", "2") != "1":
-                self._engines.append(Engine(eng.device))
-                self._engines[1].set_option("prune", 1 if eng.prune else 0)
+            if isinstance(eng, Engine):
+                self._engines += _spare_engines(eng, max(1, INFLIGHT) - 1)
             self._pool = ThreadPoolExecutor(max_workers=len(self._engines))
         while len(self._pending) >= len(self._engines):
             self._drain_one()
         eng = self._engines[self.batches_run % len(self._engines)]
+        if _TRACE:
+            import time
+            t_sub = time.perf_counter()
+            n_b = int(pack.finalize()[0].size)
+
+            def call(eng=eng, k=self.batches_run):
+                t0 = time.perf_counter()
+                out = eng.validate(pack, svs, reads, self.scoring)
+                print(f"[stage] batch {k}: {len(svs)} SVs {n_b >> 20} MB queued {1e3 * (t0 - t_sub):.1f} ms, GPU call "
+                      f"{1e3 * (time.perf_counter() - t0):.1f} ms, done at {1e3 * (time.perf_counter() - _T0):.1f}", flush=True)
+                return out
+            print(f"[stage] batch {self.batches_run} submitted at {1e3 * (t_sub - _T0):.1f} ms", flush=True)
+            fut = self._pool.submit(call)
+            self._pending.append((fut, metas, svs))
+            self.batches_run += 1
+            return
         fut = self._pool.submit(eng.validate, pack, svs, reads, self.scoring)
         self._pending.append((fut, metas, svs))
         self.batches_run += 1
@@ -577,9 +598,7 @@ class Alignment_counter(object):
         if self._pool is not None:
             self._pool.shutdown(wait=True)
             self._pool = None
-            for extra in self._engines[1:]:
-                extra.close()
-            self._engines = []
+            self._engines = []          # the extra contexts stay in the per-device pool for the next counter
         for h in (self.hout_count, self.hout_ainfo):
             if not h.closed:
                 h.close()
@@ -612,6 +631,27 @@ class Alignment_counter(object):
                               "garbage collection", RuntimeWarning)
 
 
+_SPARES: Dict[int, List[Engine]] = {}
+
+
+def _spare_engines(eng: Engine, n: int) -> List[Engine]:
+    """Extra contexts on eng's GPU for calls in flight; created once per process and device (a context allocates its
+    rings and snapshot scratch), shared by successive counters (tumor, control, single breakends ...)."""
+    pool = _SPARES.setdefault(eng.device, [])
+    pool[:] = [e for e in pool if getattr(e, "_h", None)]
+    while len(pool) < n:
+        pool.append(Engine(eng.device))
+    for e in pool[:n]:
+        if e.prune != eng.prune:
+            e.set_option("prune", 1 if eng.prune else 0)
+    return pool[:n]
+
+
+_TRACE = os.environ.get("NMSV_STAGE_TRACE") is not None      # per-batch timeline on stdout (measurement knob)
+import time as _time
+_T0 = _time.perf_counter()
+
+
 def eng_prune_probe(counter) -> Engine:
     return counter._engine or default_engine()
 
@@ -632,27 +672,62 @@ def _stream_seam_native(seam_file: str, counter: Alignment_counter, is_sbnd: boo
         if size:
             data = mmap.mmap(hin.fileno(), 0, access=mmap.ACCESS_READ)
             src = np.frombuffer(data, dtype=np.uint8)
-            gcap, rcap = 4096, 1 << 17
-            groups = np.zeros(gcap, dtype=_lib.SEAM_GROUP_DTYPE)
-            sreads = np.zeros(rcap, dtype=_lib.SEAM_READ_DTYPE)
-            ng, nr = ctypes.c_uint32(0), ctypes.c_uint32(0)
-            nxt, err = ctypes.c_uint64(0), ctypes.c_uint64(0)
-            pos = 0
-            while pos < size:
-                rc = L.nmsv_seam_scan(src.ctypes.data, size, pos, BATCH_BASES, 1 if is_sbnd else 0, groups.ctypes.data,
-                                      gcap, sreads.ctypes.data, rcap, ctypes.byref(ng), ctypes.byref(nr),
-                                      ctypes.byref(nxt), ctypes.byref(err))
-                if rc == _lib.E_CAPACITY:          # one candidate with more reads than the table holds
-                    rcap *= 2
+            # The scan is pure C with the GIL released: it runs one batch ahead on a thread of its own while this thread
+            # builds templates and tables for the previous batch.
+            import queue
+            import threading
+            q: "queue.Queue" = queue.Queue(maxsize=2)
+            stop = threading.Event()
+
+            def scanner():
+                try:
+                    gcap, rcap = 4096, 1 << 17
+                    groups = np.zeros(gcap, dtype=_lib.SEAM_GROUP_DTYPE)
                     sreads = np.zeros(rcap, dtype=_lib.SEAM_READ_DTYPE)
-                    continue
-                if rc != 0:
-                    line_no = data[:err.value].count(b"\n") + 1
-                    raise ValueError(f"{seam_file}: line {line_no} is not `key, read id, mapq1, mapq2, sequence` (5 tab-separated "
-                                     "fields, integer or None mapping qualities)")
-                if ng.value:
-                    counter._submit_scanned(data, src, groups[:ng.value].copy(), sreads[:nr.value].copy(), is_sbnd)
-                pos = nxt.value
+                    ng, nr = ctypes.c_uint32(0), ctypes.c_uint32(0)
+                    nxt, err = ctypes.c_uint64(0), ctypes.c_uint64(0)
+                    pos = 0
+                    n_batches = 0
+                    while pos < size and not stop.is_set():
+                        # the first batches are smaller: the GPU starts after a quarter of a batch has been parsed
+                        want = max(BATCH_BASES >> max(2 - n_batches, 0), 1)
+                        rc = L.nmsv_seam_scan(src.ctypes.data, size, pos, want, BATCH_BASES // 2, 1 if is_sbnd else 0,
+                                              groups.ctypes.data, gcap, sreads.ctypes.data, rcap, ctypes.byref(ng),
+                                              ctypes.byref(nr), ctypes.byref(nxt), ctypes.byref(err))
+                        if rc == _lib.E_CAPACITY:          # one candidate with more reads than the table holds
+                            rcap *= 2
+                            sreads = np.zeros(rcap, dtype=_lib.SEAM_READ_DTYPE)
+                            continue
+                        if rc != 0:
+                            line_no = data[:err.value].count(b"\n") + 1
+                            raise ValueError(f"{seam_file}: line {line_no} is not `key, read id, mapq1, mapq2, sequence` (5 "
+                                             "tab-separated fields, integer or None mapping qualities)")
+                        if ng.value:
+                            q.put((groups[:ng.value].copy(), sreads[:nr.value].copy()))
+                            n_batches += 1
+                        pos = nxt.value
+                    q.put(None)
+                except BaseException as exc:      # handed to the consumer
+                    q.put(exc)
+
+            th = threading.Thread(target=scanner, daemon=True)
+            th.start()
+            try:
+                while True:
+                    item = q.get()
+                    if item is None:
+                        break
+                    if isinstance(item, BaseException):
+                        raise item
+                    counter._submit_scanned(data, src, item[0], item[1], is_sbnd)
+            finally:                    # on an error: let the scanner run out instead of blocking on a full queue
+                stop.set()
+                while th.is_alive():
+                    try:
+                        q.get(timeout=0.05)
+                    except queue.Empty:
+                        pass
+                th.join()
     counter.close()          # waits for the batches in flight: their tables keep the mapping alive until then
 
 

@@ -383,7 +383,7 @@ static bool seam_mapq(const char* p, const char* e, int32_t* out)
     return true;
 }
 
-extern "C" int nmsv_seam_scan(const char* data, uint64_t size, uint64_t start, uint64_t max_bases, int is_sbnd,
+extern "C" int nmsv_seam_scan(const char* data, uint64_t size, uint64_t start, uint64_t max_bases, uint64_t tail_bytes, int is_sbnd,
                               nmsv_seam_group* groups, uint32_t group_cap, nmsv_seam_read* reads, uint32_t read_cap,
                               uint32_t* n_groups, uint32_t* n_reads, uint64_t* next, uint64_t* error_off)
 {
@@ -487,7 +487,7 @@ extern "C" int nmsv_seam_scan(const char* data, uint64_t size, uint64_t start, u
         g.read_begin = first_read; g.read_end = nr; g.reserved = 0;
         bases += group_bases;
         if (pos > size) pos = size;
-        if (bases >= max_bases) break;
+        if (bases >= max_bases && size - std::min(pos, size) >= tail_bytes) break;      // a short rest joins this batch
     }
     *n_groups = ng; *n_reads = nr; *next = pos > size ? size : pos;
     return NMSV_OK;

@@ -219,7 +219,8 @@ def test_byte_level_seam_reader_builds_the_same_batches(tmp_path, monkeypatch, s
         fc, fi = str(tmp_path / f"native{batch_bases}.count"), str(tmp_path / f"native{batch_bases}.info")
         C.count_sread_from_seam(seam, fc, fi, wl.fasta, sbnd, 40, 1.2, engine=eng)
         ref_batches, ref_count = out[("lines", batch_bases)]
-        assert open(fc).read() == ref_count and len(eng.batches) == len(ref_batches)
+        assert open(fc).read() == ref_count       # (the scan starts with smaller batches: their number may differ)
+        assert (len(eng.batches) > 1) == (len(ref_batches) > 1)
         assert canonical(eng.batches) == canonical(ref_batches)
         assert any(int(o) == _lib.SEQ_ABSENT for b in eng.batches for o in b[1])
     # the extra lines did what they are there for
