@@ -78,11 +78,15 @@ def _ssw(s1, s2, gap_open, gap_extend, matrix):
     return O.ssw(s1, s2, gap_open, gap_extend, matrix.match, matrix.mismatch)      # fields score1, read_begin1, ... ; None on saturation
 
 
-def load_reference():
+def load_reference(real_parasail=None):
+    """real_parasail: an imported parasail module to use instead of the oracle-backed stand-in (tests/test_vs_parasail.py
+    re-runs the reference with the real engine wherever it is installed)."""
     pysam = types.ModuleType("pysam")
     pysam.AlignmentFile, pysam.FastaFile = _AlignmentFile, _FastaFile
-    parasail = types.ModuleType("parasail")
-    parasail.matrix_create, parasail.ssw = (lambda a, m, x: _Matrix(a, m, x)), _ssw
+    parasail = real_parasail
+    if parasail is None:
+        parasail = types.ModuleType("parasail")
+        parasail.matrix_create, parasail.ssw = (lambda a, m, x: _Matrix(a, m, x)), _ssw
     sys.modules["pysam"], sys.modules["parasail"] = pysam, parasail
     pkg = types.ModuleType("nanomonsv")                 # the package without its __init__ (which would pull in the CLI)
     pkg.__path__ = ["/root/reference/nanomonsv"]

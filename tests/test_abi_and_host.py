@@ -255,3 +255,23 @@ def test_device_pick_follows_env_then_pool_worker(monkeypatch):
     monkeypatch.setattr(engine._lib, "load", lambda: FakeLib())
     monkeypatch.setattr(multiprocessing.current_process(), "_identity", (11,), raising=False)
     assert engine.pick_device() == (11 - 1) % 8
+
+
+def test_window_subsampling_equals_the_reference_draws():
+    """bam_subsample_fetch (reference :11-23): above max_read_num reads in a window a random subset is kept. The reference
+    draws unseeded; with the same seed the mirror must keep exactly the reads the reference's own function kept
+    (tests/golden/subsample_vectors.json, incl. the > 500-read branch), in file order."""
+    import json
+    import random
+    vec = json.load(open(os.path.join(ROOT, "tests", "golden", "subsample_vectors.json")))["cases"]
+
+    class Handle:
+        def __init__(self, n):
+            self.n = n
+
+        def fetch(self, chrom, start, end):
+            return iter(range(self.n))
+    assert any(c["n"] > 500 and len(c["kept"]) == 500 for c in vec)
+    for c in vec:
+        random.seed(c["seed"])
+        assert list(C.bam_subsample_fetch(Handle(c["n"]), "chr1", 0, 200, c["max_read_num"])) == c["kept"], c["n"]
