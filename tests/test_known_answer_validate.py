@@ -29,7 +29,7 @@ def test_validate_known_answer(engine, tmp_path):
     for sample, bam in (("tumor", os.environ[NEED[0]]), ("control", os.environ[NEED[1]])):
         fc, fi = str(tmp_path / f"{sample}.sread_count.txt"), str(tmp_path / f"{sample}.sread_info.txt")
         count_sread_by_alignment(str(sv_list), bam, fc, fi, os.environ[NEED[2]], var_read_min_mapq=40, use_ssw_lib=False,
-                                 sort_option="", debug=False, engine=engine)
+                                 sort_option="-S 2G", debug=False, engine=engine)      # arg_parser.py:203
         f = open(fc).read().splitlines()[0].split("\t")
         assert f[:8] == rec[:8]
         got[sample] = (int(f[8]), int(f[9]))
