@@ -812,9 +812,12 @@ def count_sread_by_alignment(sv_file, alignment_file, output_count_file, output_
                              sbnd_file=None, output_count_file_sbnd=None, output_alignment_info_file_sbnd=None,
                              check_read_max_num=500, var_read_min_mapq=0, score_ratio_thres=1.2, use_ssw_lib=False,
                              sort_option=None, debug=False, engine: Optional[Engine] = None):
-    """Same signature as the reference (:401-403) plus an optional engine handle. NMSV_DIRECT_GATHER=1 keeps the gathered
-    reads in memory instead of going through the sorted seam file (gather_reads_direct)."""
-    if os.environ.get("NMSV_DIRECT_GATHER", "0") == "1":
+    """Same signature as the reference (:401-403) plus an optional engine handle. By default the gathered reads stay in
+    memory (gather_reads_direct: no seam TSV of whole reads per key, no GNU sort of it, no re-parse; a read that serves
+    several candidates is packed once; reads whose mapq test fails are not packed at all). With debug=True -- where the
+    reference leaves its `.tmp.local_read_for_realignment` file behind -- or NMSV_DIRECT_GATHER=0 the reference's own
+    route through the sorted seam file is taken; both routes hand the GPU the same work and write the same files."""
+    if os.environ.get("NMSV_DIRECT_GATHER", "0" if debug else "1") == "1":
         groups, groups_sbnd = gather_reads_direct(sv_file, alignment_file, reference_fasta, sbnd_file=sbnd_file,
                                                   sort_option=sort_option)
         _count_from_groups(groups, Alignment_counter(output_count_file, output_alignment_info_file, reference_fasta,
