@@ -35,10 +35,13 @@ def main():
     probs = problems(n)
     cells = sum((len(c) + 1) * (len(a) + len(b) + 2) for c, a, b in probs)
     SW.sw_jump_batch(probs[:64], 1, 3, 3, 2, 10, engine=eng)
+    if os.environ.get("NMSV_JUMP_WARM"):      # grow the stream-ordered pool once (a long-running process has done so)
+        SW.sw_jump_batch(probs, 1, 3, 3, 2, 10, engine=eng)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     got = SW.sw_jump_batch(probs, 1, 3, 3, 2, 10, engine=eng)
     dt = time.perf_counter() - t0
+    dt_abi = SW.sw_jump_batch.last_abi_seconds
     k = min(40, n)
     t1 = time.perf_counter()
     exp = [O.sw_jump(c, a, b, 1, 3, 3, 2, 10) for c, a, b in probs[:k]]
@@ -47,6 +50,7 @@ def main():
     cells_k = sum((len(c) + 1) * (len(a) + len(b) + 2) for c, a, b in probs[:k])
     print(json.dumps({"metric": "sw_jump cells/s (end to end through nmsv_sw_jump_batch, host strings in and out)",
                       "problems": n, "cells": cells, "gpu_seconds": dt, "gpu_gcells_per_s": cells / dt / 1e9,
+                      "abi_seconds": dt_abi, "abi_gcells_per_s": cells / dt_abi / 1e9,
                       "problems_per_s": n / dt, "found": sum(g is not None for g in got),
                       "cpu_port_1core_gcells_per_s": cells_k / dt_cpu / 1e9,
                       "reference_python_gcells_per_s": 8e-5, "device": eng.device_info()["name"]}))

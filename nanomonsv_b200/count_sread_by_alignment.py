@@ -818,6 +818,9 @@ def count_sread_by_alignment(sv_file, alignment_file, output_count_file, output_
     reference leaves its `.tmp.local_read_for_realignment` file behind -- or NMSV_DIRECT_GATHER=0 the reference's own
     route through the sorted seam file is taken; both routes hand the GPU the same work and write the same files."""
     if os.environ.get("NMSV_DIRECT_GATHER", "0" if debug else "1") == "1":
+        for stale in (output_count_file, output_count_file_sbnd):      # the reference rewrites and removes its seam files
+            if stale is not None and os.path.exists(stale + ".tmp.local_read_for_realignment"):
+                os.remove(stale + ".tmp.local_read_for_realignment")
         groups, groups_sbnd = gather_reads_direct(sv_file, alignment_file, reference_fasta, sbnd_file=sbnd_file,
                                                   sort_option=sort_option)
         _count_from_groups(groups, Alignment_counter(output_count_file, output_alignment_info_file, reference_fasta,

@@ -220,6 +220,9 @@ extern "C" int nmsv_create(nmsv_ctx** out, int device)
     CREATE_TRY(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     for (int c = 0; c < kNumClasses; ++c) CREATE_TRY(setup_class_idx(c, &ctx->blocks_per_sm[c]));
+    // block-per-problem sw_jump kernel: three diagonals of the longest region it accepts (set once, not per call)
+    CREATE_TRY(cudaFuncSetAttribute(sw_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(3ull * (kJumpMaxRegion + 2) * sizeof(int32_t))));
     {
         int g = 0;
         for (int c = 0; c < kNumClasses; ++c) g = std::max(g, ctx->prop.multiProcessorCount * std::max(1, ctx->blocks_per_sm[c]));
@@ -1671,7 +1674,10 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
 
-    std::vector<JumpProblem> probs(n_problems);
+    // Regions of up to kJumpWarpMaxRegion columns (every locate_bp call: +-20 bp around a read-supported breakpoint range, or
+    // the first / last 500 bases of a contig) run one warp per problem; longer ones keep one block per problem.
+    std::vector<JumpProblem> probs;
+    std::vector<JumpWarpProblem> wprobs;
     uint64_t ops_total = 0;
     uint32_t max_region = 0;
     for (uint32_t i = 0; i < n_problems; ++i) {
@@ -1680,24 +1686,28 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
             return set_err(ctx, NMSV_E_INVALID, "sw_jump problem %u: sequence index out of range", i);
         if (lens[a] > (uint32_t)kJumpMaxRegion || lens[b] > (uint32_t)kJumpMaxRegion)
             return set_err(ctx, NMSV_E_RANGE, "sw_jump problem %u: region longer than %d", i, kJumpMaxRegion);
-        JumpProblem& p = probs[i];
-        p.c_off = offsets[c]; p.r1_off = offsets[a]; p.r2_off = offsets[b];
-        p.n = lens[c]; p.m1 = lens[a]; p.m2 = lens[b]; p.pad = 0;
-        p.ops_off = ops_total;
-        ops_total += 2ull * p.n + p.m1 + p.m2 + 4;
-        max_region = std::max(max_region, std::max(p.m1, p.m2));
+        if (std::max(lens[a], lens[b]) <= (uint32_t)kJumpWarpMaxRegion) {
+            JumpWarpProblem p;
+            p.c_off = offsets[c]; p.r1_off = offsets[a]; p.r2_off = offsets[b];
+            p.n = lens[c]; p.m1 = lens[a]; p.m2 = lens[b]; p.res_idx = i;
+            p.w1_off = p.w2_off = p.row_off = 0;
+            p.ops_off = ops_total;
+            wprobs.push_back(p);
+        } else {
+            JumpProblem p;
+            p.c_off = offsets[c]; p.r1_off = offsets[a]; p.r2_off = offsets[b];
+            p.n = lens[c]; p.m1 = lens[a]; p.m2 = lens[b]; p.res_idx = i;
+            p.ops_off = ops_total;
+            max_region = std::max(max_region, std::max(p.m1, p.m2));
+            probs.push_back(p);
+        }
+        ops_total += 2ull * lens[c] + lens[a] + lens[b] + 4;
     }
     if (ops_total > ops_capacity)
         return set_err(ctx, NMSV_E_CAPACITY, "ops buffer holds %llu bytes, %llu needed", (unsigned long long)ops_capacity,
                        (unsigned long long)ops_total);
 
-    const size_t smem = 3ull * (max_region + 2) * sizeof(int32_t);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(sw_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-    int bps = 0;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sw_jump_kernel, kJumpThreads, smem));
-    const uint32_t max_blocks = (uint32_t)ctx->prop.multiProcessorCount * (uint32_t)std::max(1, bps);
-
-    DevBuf d_bytes, d_log, d_probs, d_paths, d_rows, d_res, d_ops;
+    DevBuf d_bytes, d_log, d_probs, d_paths, d_rows, d_res, d_ops, d_next;
     CUDA_TRY(ctx, d_bytes.alloc(n_bytes, s));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_bytes.p, bytes, n_bytes, cudaMemcpyHostToDevice, s));
     if (log_table && log_table_len) {
@@ -1706,17 +1716,67 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
     }
     CUDA_TRY(ctx, d_res.alloc(sizeof(JumpResult) * (size_t)n_problems, s));
     CUDA_TRY(ctx, d_ops.alloc(ops_total, s));
+    const uint64_t kMaxWorkBytes = 6ull << 30;       // workspace per launch
 
-    // process the problems in chunks whose path workspace stays below ~6 GB
-    const uint64_t kMaxPathBytes = 6ull << 30;
+    // ---- warp-per-problem kernel, longest problems first, in chunks whose workspace stays below the limit
+    std::stable_sort(wprobs.begin(), wprobs.end(), [](const JumpWarpProblem& x, const JumpWarpProblem& y) {
+        return (uint64_t)x.n * (x.m1 + x.m2) > (uint64_t)y.n * (y.m1 + y.m2); });
+    for (size_t first = 0; first < wprobs.size();) {
+        uint64_t words = 0;
+        size_t last = first;
+        while (last < wprobs.size()) {
+            JumpWarpProblem& p = wprobs[last];
+            const uint64_t rows = (uint64_t)p.n + 1;
+            const uint64_t need = 64 * rows + 2 * rows + 2 + 2 * rows;      // two word matrices, rowbest, prefix (+pad), rowinfo
+            if (last > first && (words + need) * 8 > kMaxWorkBytes) break;
+            p.w1_off = words; p.w2_off = words + 32 * rows; p.row_off = words + 64 * rows;
+            words += need;
+            ++last;
+        }
+        const uint32_t cnt = (uint32_t)(last - first);
+        CUDA_TRY(ctx, d_rows.alloc(words * 8, s));
+        CUDA_TRY(ctx, d_probs.alloc(sizeof(JumpWarpProblem) * (size_t)cnt, s));
+        CUDA_TRY(ctx, d_next.alloc(sizeof(uint32_t), s));
+        CUDA_TRY(ctx, cudaMemsetAsync(d_next.p, 0, sizeof(uint32_t), s));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_probs.p, wprobs.data() + first, sizeof(JumpWarpProblem) * (size_t)cnt, cudaMemcpyHostToDevice, s));
+        JumpWarpParams wp;
+        wp.bytes = d_bytes.as<uint8_t>(); wp.problems = d_probs.as<JumpWarpProblem>(); wp.n_problems = cnt;
+        wp.next = d_next.as<uint32_t>(); wp.work = d_rows.as<unsigned long long>();
+        wp.logtab = d_log.as<double>(); wp.logtab_len = (log_table && log_table_len) ? log_table_len : 0;
+        wp.results = d_res.as<JumpResult>(); wp.ops = d_ops.as<uint8_t>();
+        wp.match = params->match_score; wp.mismatch_penalty = params->mismatch_penalty; wp.gap_cost = params->gap_cost;
+        wp.jump_cost = params->jump_cost; wp.minimum_score = params->minimum_score;
+        const uint32_t blocks = std::min<uint32_t>((cnt + kJumpWarpsPerBlock - 1) / kJumpWarpsPerBlock,
+                                                   (uint32_t)ctx->prop.multiProcessorCount * 8u);
+        static const bool jtrace = getenv("NMSV_TRACE") != nullptr;
+        const auto jt0 = std::chrono::steady_clock::now();
+        if (jtrace) cudaStreamSynchronize(s);
+        const auto jt1 = std::chrono::steady_clock::now();
+        sw_jump_warp_kernel<<<blocks, kJumpWarpsPerBlock * 32, 0, s>>>(wp);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaStreamSynchronize(s));      // the host-side problem table of this chunk may be reused
+        if (jtrace)
+            fprintf(stderr, "[nmsv] sw_jump: %u problems, workspace %.1f MB, setup %.2f ms, warp kernel %.2f ms\n", cnt, words * 8 / 1e6,
+                    std::chrono::duration<double, std::milli>(jt1 - jt0).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - jt1).count());
+        first = last;
+    }
+
+    // ---- block-per-problem kernel for the long regions
+    const size_t smem = 3ull * (max_region + 2) * sizeof(int32_t);
+    int bps = 1;
+    if (!probs.empty())
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, sw_jump_kernel, kJumpThreads, smem));
+    const uint32_t max_blocks = (uint32_t)ctx->prop.multiProcessorCount * (uint32_t)std::max(1, bps);
+    const uint32_t n_slow = (uint32_t)probs.size();
     uint32_t first = 0;
-    while (first < n_problems) {
+    while (first < n_slow) {
         uint64_t path_bytes = 0, row_words = 0;
         uint32_t last = first;
-        while (last < n_problems) {
+        while (last < n_slow) {
             JumpProblem& p = probs[last];
             const uint64_t pb = (uint64_t)(p.n + 1) * (p.m1 + 1) + (uint64_t)(p.n + 1) * (p.m2 + 1);
-            if (last > first && path_bytes + pb > kMaxPathBytes) break;
+            if (last > first && path_bytes + pb > kMaxWorkBytes) break;
             p.p1_off = path_bytes;
             p.p2_off = path_bytes + (uint64_t)(p.n + 1) * (p.m1 + 1);
             path_bytes += pb;
@@ -1733,7 +1793,7 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
         jp.bytes = d_bytes.as<uint8_t>(); jp.problems = d_probs.as<JumpProblem>(); jp.n_problems = cnt;
         jp.paths = d_paths.as<uint8_t>(); jp.rows = d_rows.as<unsigned long long>();
         jp.logtab = d_log.as<double>(); jp.logtab_len = (log_table && log_table_len) ? log_table_len : 0;
-        jp.results = d_res.as<JumpResult>() + first; jp.ops = d_ops.as<uint8_t>();
+        jp.results = d_res.as<JumpResult>(); jp.ops = d_ops.as<uint8_t>();
         jp.match = params->match_score; jp.mismatch_penalty = params->mismatch_penalty; jp.gap_cost = params->gap_cost;
         jp.jump_cost = params->jump_cost; jp.minimum_score = params->minimum_score;
         sw_jump_kernel<<<std::min(cnt, max_blocks), kJumpThreads, smem, s>>>(jp);

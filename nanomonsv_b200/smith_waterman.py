@@ -68,10 +68,13 @@ def sw_jump_batch(problems: Sequence[Tuple[str, str, str]], match_score: int = 1
     with np.errstate(divide="ignore"):
         logtab = np.log(np.arange(int(lens[0::3].max()) + 1))      # numpy's log, like the reference (:40)
     prm = _lib.JumpParams(match_score, mismatch_penalty, gap_cost, jump_cost, minimum_score)
+    import time
+    t0 = time.perf_counter()
     eng._check(eng._L.nmsv_sw_jump_batch(eng._h, data.ctypes.data, data.size, offsets.ctypes.data, lens.ctypes.data,
                                          len(lens), cidx.ctypes.data, aidx.ctypes.data, bidx.ctypes.data, n,
                                          ctypes.byref(prm), logtab.ctypes.data, len(logtab), out.ctypes.data,
                                          ops.ctypes.data, ops.size))
+    sw_jump_batch.last_abi_seconds = time.perf_counter() - t0      # the C-ABI call alone (H2D, kernels, D2H), for bench_jump.py
     res: List[Optional[tuple]] = []
     for k, (contig, r1, r2) in enumerate(problems):
         r = out[k]

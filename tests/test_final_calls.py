@@ -64,4 +64,4 @@ def test_gpu_count_files_are_the_inputs_of_the_reference_final_calls(engine, tmp
         written[sample] = open(str(seam) + ".count").read().splitlines()
     assert written["tumor"] == integ["tumor_count"] and written["control"] == integ["control_count"]
     calls = [l for l in {c["name"]: c for c in integ["cases"]}["tumor_and_control"]["result"][1:] if l.endswith("PASS")]
-    assert len(calls) == 4
+    assert len(calls) == 3 and len({c["name"]: c for c in integ["cases"]}["tumor_and_control"]["result"]) - 1 == 4
