@@ -32,7 +32,10 @@ def ssw_check_parasail(query, target, engine: Optional[Engine] = None):
 
 
 def ssw_check_ssw_lib(query, target, engine: Optional[Engine] = None):
-    """long_read_validate.py:20-123 (libssw route; its strand rule and coordinates equal the parasail route)."""
+    """long_read_validate.py:20-123, the libssw route (dead code in the reference: its CLI flag is commented out,
+    arg_parser.py:124-125). The host side of that route -- strand rule, coordinate conversion (:102-113) -- is the same as
+    the parasail route's; that libssw's ssw_align(flag=1, maskLen=m/2) returns the same cells as parasail.ssw is NOT
+    verified here (libssw is not in this image): this name runs the same CUDA engine as ssw_check_parasail."""
     return _ssw_check_gpu(query, target, True, engine=engine)
 
 
