@@ -275,3 +275,74 @@ def test_window_subsampling_equals_the_reference_draws():
     for c in vec:
         random.seed(c["seed"])
         assert list(C.bam_subsample_fetch(Handle(c["n"]), "chr1", 0, 200, c["max_read_num"])) == c["kept"], c["n"]
+
+
+def _scan_all(data: bytes, max_bases, tail_bytes, is_sbnd, gcap, rcap):
+    """Drive nmsv_seam_scan over a whole buffer the way the stage function does; returns [(key, [(id, seq, m1, m2)])]."""
+    L = _lib.load()
+    src = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(1, dtype=np.uint8)
+    groups = np.zeros(gcap, dtype=_lib.SEAM_GROUP_DTYPE)
+    reads = np.zeros(rcap, dtype=_lib.SEAM_READ_DTYPE)
+    ng, nr, nxt, err = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+    pos, out, calls = 0, [], 0
+    while pos < len(data):
+        rc = L.nmsv_seam_scan(src.ctypes.data, len(data), pos, max_bases, tail_bytes, is_sbnd, groups.ctypes.data, gcap,
+                              reads.ctypes.data, rcap, ctypes.byref(ng), ctypes.byref(nr), ctypes.byref(nxt), ctypes.byref(err))
+        if rc != 0:
+            return rc, err.value
+        assert nxt.value > pos and ng.value >= 1
+        for g in groups[:ng.value]:
+            rows = []
+            for r in reads[int(g["read_begin"]):int(g["read_end"])]:
+                rows.append((data[int(r["id_off"]):int(r["id_off"]) + int(r["id_len"])].decode(),
+                             data[int(r["seq_off"]):int(r["seq_off"]) + int(r["seq_len"])].decode(), int(r["mapq1"]), int(r["mapq2"])))
+            out.append((data[int(g["key_off"]):int(g["key_off"]) + int(g["key_len"])].decode(), rows))
+        pos = nxt.value
+        calls += 1
+    return out, calls
+
+
+def test_seam_scan_grouping_capacity_and_errors():
+    """nmsv_seam_scan: whole key groups per call, the dict semantics of the reference for repeated read ids, batch cuts by
+    bases, by table capacity and by the short-rest rule, error offsets -- against a Python restatement of the loop."""
+    import random
+    rnd = random.Random(11)
+    lines, expect = [], []
+    for k in range(23):
+        key = f"chr{k % 3},{1000 + k},+,chr1,{5000 + k},-,---,r_{k}"
+        order, seqs, mq = [], {}, {}
+        for r in range(rnd.randint(1, 9)):
+            rid = f"read{rnd.randint(0, 5)}"
+            seq = "" if rnd.random() < 0.15 else "".join(rnd.choice("ACGTNacgt") for _ in range(rnd.randint(1, 60)))
+            m1 = "None" if rnd.random() < 0.2 else str(rnd.randint(0, 60))
+            m2 = "None" if rnd.random() < 0.2 else str(rnd.randint(0, 60))
+            lines.append(f"{key}\t{rid} extra words\t{m1}\t{m2}\t {seq} ")
+            if rid in seqs or seq:
+                mq[rid] = (m1, m2)
+            if seq:
+                if rid not in seqs:
+                    order.append(rid)
+                seqs[rid] = seq
+        conv = lambda v: -1 if v == "None" else int(v)   # noqa: E731
+        if order:
+            expect.append((key, [(rid, seqs[rid], conv(mq[rid][0]), conv(mq[rid][1])) for rid in order]))
+    data = ("\r\n".join(lines)).encode()                 # CR LF, no newline at the end
+    ref, _ = _scan_all(data, 1 << 40, 0, 0, 4096, 4096)
+    assert [g for g in ref if g[1]] == expect and len(ref) == 23      # a group whose reads are all empty still exists (0 reads)
+    # cut by bases: several calls, same content; by tiny tables: same content; short rest joins the last batch
+    for args in ((200, 0, 64, 64), (1 << 40, 0, 2, 4096), (1 << 40, 0, 4096, 12), (150, 10 ** 9, 4096, 4096)):
+        got, calls = _scan_all(data, args[0], args[1], 0, args[2], args[3])
+        assert got == ref, args
+        assert calls == 1 if args[1] else calls > 1
+    # single-breakend files: the fourth column is ignored (None)
+    sb, _ = _scan_all(data, 1 << 40, 0, 1, 4096, 4096)
+    assert all(r[3] == -1 for g in sb for r in g[1]) and [(g[0], [r[:3] for r in g[1]]) for g in sb] == [(g[0], [r[:3] for r in g[1]]) for g in ref]
+    # one group larger than the read table: NMSV_E_CAPACITY (the caller grows the table)
+    assert _scan_all(data, 1 << 40, 0, 0, 4096, 1)[0] == _lib.E_CAPACITY
+    # malformed lines: NMSV_E_INVALID with the offset of the line
+    bad = data + b"\nkey\tid\tnot_a_number\t3\tACGT\n"
+    rc, off = _scan_all(bad, 1 << 40, 0, 0, 4096, 4096)
+    assert rc == _lib.E_INVALID and bad[off:off + 3] == b"key"
+    rc, off = _scan_all(b"only\tfour\t1\t2\n", 1 << 40, 0, 0, 16, 16)
+    assert rc == _lib.E_INVALID and off == 0
+    assert _scan_all(b"", 1, 0, 0, 4, 4) == ([], 0)

@@ -24,4 +24,5 @@ for _ in range(3):
     best = min(best, [ms for n_, r, ms in kt if n_ == "sw_forward"][0])
 plan.download()
 st = plan.stats()
+print({k: st[k] for k in ("cells_reference", "cells_dedup", "cells_executed", "cells_pruned", "cells_begin", "fwd_tasks", "fwd_tasks_queued", "rev_tasks", "reads_pruned")}, file=sys.stderr)
 print(os.environ.get("NMSV_PRUNE"), os.environ.get("NMSV_SPAWN_FIRST"), n, os.environ.get("NMSV_LIB_PATH"), "fwd_ms", round(best, 2), "gcups_exec", round(st["cells_executed"] / best / 1e6))
