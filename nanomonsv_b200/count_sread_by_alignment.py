@@ -467,23 +467,26 @@ class Alignment_counter(object):
         while len(self._pending) >= len(self._engines):
             self._drain_one()
         eng = self._engines[self.batches_run % len(self._engines)]
-        if _TRACE:
-            import time
-            t_sub = time.perf_counter()
-            n_b = int(pack.finalize()[0].size)
+        import time
+        t_sub = time.perf_counter()
+        scoring = self.scoring       # the closure must not hold `self`: a counter whose last reference dies on a worker
+                                     # thread would run close() there and wait for that very thread
 
-            def call(eng=eng, k=self.batches_run):
-                t0 = time.perf_counter()
-                out = eng.validate(pack, svs, reads, self.scoring)
-                print(f"[stage] batch {k}: {len(svs)} SVs {n_b >> 20} MB queued {1e3 * (t0 - t_sub):.1f} ms, GPU call "
-                      f"{1e3 * (time.perf_counter() - t0):.1f} ms, done at {1e3 * (time.perf_counter() - _T0):.1f}", flush=True)
-                return out
+        def call(eng=eng, k=self.batches_run):
+            # `pack` may be a callable that encodes and packs the sequences: that work (C, GIL released) then runs on the
+            # worker thread too, beside the caller's parsing
+            t0 = time.perf_counter()
+            the_pack = pack() if callable(pack) else pack
+            t1 = time.perf_counter()
+            out = eng.validate(the_pack, svs, reads, scoring)
+            if _TRACE:
+                print(f"[stage] batch {k}: {len(svs)} SVs {int(the_pack.finalize()[0].size) >> 20} MB queued "
+                      f"{1e3 * (t0 - t_sub):.1f} ms, pack {1e3 * (t1 - t0):.1f} ms, GPU call {1e3 * (time.perf_counter() - t1):.1f} ms, "
+                      f"done at {1e3 * (time.perf_counter() - _T0):.1f}", flush=True)
+            return out
+        if _TRACE:
             print(f"[stage] batch {self.batches_run} submitted at {1e3 * (t_sub - _T0):.1f} ms", flush=True)
-            fut = self._pool.submit(call)
-            self._pending.append((fut, metas, svs))
-            self.batches_run += 1
-            return
-        fut = self._pool.submit(eng.validate, pack, svs, reads, self.scoring)
+        fut = self._pool.submit(call)
         self._pending.append((fut, metas, svs))
         self.batches_run += 1
 
@@ -544,31 +547,34 @@ class Alignment_counter(object):
             keep &= (m2 != _lib.MAPQ_NONE) & (m2 >= self.var_read_min_mapq)
         if not getattr(eng_prune_probe(self), "prune", True):
             keep[:] = True
-        present = np.ones(nt + nr, dtype=bool)
-        present[nt:] = keep
-        padded = np.where(present, (lens.astype(np.uint64) + np.uint64(15)) & ~np.uint64(15), np.uint64(0))
-        offsets = np.zeros(nt + nr, dtype=np.uint64)
-        if nt + nr > 1:
-            np.cumsum(padded[:-1], out=offsets[1:])
-        total = int(offsets[-1] + padded[-1]) if nt + nr else 0
-        codes = np.empty(total, dtype=np.uint8)          # every byte is written below (sequences + their padding)
-        for i, c in enumerate(tmpl_codes):
-            o = int(offsets[i])
-            codes[o:o + len(c)] = c
-            codes[o + len(c):o + int(padded[i])] = 4
-        kidx = np.flatnonzero(keep)
-        if len(kidx):
-            so = np.ascontiguousarray(sreads["seq_off"][kidx])
-            ln = np.ascontiguousarray(sreads["seq_len"][kidx])
-            do = np.ascontiguousarray(offsets[nt + kidx])
-            _lib.load().nmsv_encode_pack_padded(src.ctypes.data, so.ctypes.data, ln.ctypes.data, do.ctypes.data, len(kidx),
-                                                codes.ctypes.data)
-        offsets[nt:][~keep] = _lib.SEQ_ABSENT
+        def build_pack():        # runs on the worker thread of this batch (numpy and C: the GIL is released for most of it)
+            present = np.ones(nt + nr, dtype=bool)
+            present[nt:] = keep
+            padded = np.where(present, (lens.astype(np.uint64) + np.uint64(15)) & ~np.uint64(15), np.uint64(0))
+            offsets = np.zeros(nt + nr, dtype=np.uint64)
+            if nt + nr > 1:
+                np.cumsum(padded[:-1], out=offsets[1:])
+            total = int(offsets[-1] + padded[-1]) if nt + nr else 0
+            codes = np.empty(total, dtype=np.uint8)          # every byte is written below (sequences + their padding)
+            for i, c in enumerate(tmpl_codes):
+                o = int(offsets[i])
+                codes[o:o + len(c)] = c
+                codes[o + len(c):o + int(padded[i])] = 4
+            kidx = np.flatnonzero(keep)
+            if len(kidx):
+                so = np.ascontiguousarray(sreads["seq_off"][kidx])
+                ln = np.ascontiguousarray(sreads["seq_len"][kidx])
+                do = np.ascontiguousarray(offsets[nt + kidx])
+                _lib.load().nmsv_encode_pack_padded(src.ctypes.data, so.ctypes.data, ln.ctypes.data, do.ctypes.data, len(kidx),
+                                                    codes.ctypes.data)
+            offsets[nt:][~keep] = _lib.SEQ_ABSENT
+            return SeqPack.from_arrays(codes, offsets, lens)
+
         reads = np.zeros(nr, dtype=_lib.READ_DTYPE)
         reads["seq"] = nt + np.arange(nr, dtype=np.uint32)
         reads["sv"] = np.repeat(np.arange(ng, dtype=np.uint32), (groups["read_end"] - groups["read_begin"]).astype(np.int64))
         reads["mapq1"], reads["mapq2"] = m1, (_lib.MAPQ_NONE if is_sbnd else m2)
-        self._launch(SeqPack.from_arrays(codes, offsets, lens), svs, reads, metas)
+        self._launch(build_pack, svs, reads, metas)
 
     def _drain(self):
         """Wait for the batches in flight and write their count / info lines, in submission order."""
@@ -596,7 +602,9 @@ class Alignment_counter(object):
     def close(self):
         self.flush()
         if self._pool is not None:
-            self._pool.shutdown(wait=True)
+            import threading
+            on_worker = threading.current_thread() in getattr(self._pool, "_threads", ())      # (garbage collection there)
+            self._pool.shutdown(wait=not on_worker)
             self._pool = None
             self._engines = []          # the extra contexts stay in the per-device pool for the next counter
         for h in (self.hout_count, self.hout_ainfo):
