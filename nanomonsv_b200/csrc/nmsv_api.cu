@@ -583,7 +583,8 @@ enum : uint32_t { kCntFwdQueue = 0, kCntRevQueue = 8, kCntRecords = 17, kCntStat
 enum : uint32_t { kCellsFwd = 0, kCellsBegin = 1, kTasksSpawnedFwd = 2, kCellsTotal = 4 };
 enum : uint8_t { kReadCandidate = 1, kReadSupporting = 2,
                  kReadPruned = 4,      // mapq test already failed: counted as checked, never aligned (:344-346, :388-389)
-                 kReadVarDone = 8 };   // lazy reference alleles: the variant alignments passed, ref1/ref2 are queued
+                 kReadVarDone = 8,     // lazy reference alleles: the variant tests passed, the first reference allele is queued
+                 kReadRef1Done = 16 }; // ... the margin test against it passed too, the second one is queued
 
 __device__ __forceinline__ int alias_of(const nmsv_sv& sv, int s)
 {
@@ -742,22 +743,37 @@ __device__ __forceinline__ Sel select_strand(const SwResult* fwd_slot)
 
 // The decision for one read once the forward alignments it is waiting for are known. Runs either as a thread of
 // decide_kernel or, on the fused path, on lane 0 of the warp that finished the read's last outstanding forward task.
-// With lazy_refs it runs twice for a read whose SV has reference-allele slots: after the variant alignments (stage 1:
-// variant tests; a read that passes gets its ref1/ref2 alignments queued) and after those (stage 2).
+// With lazy_refs it runs up to three times for a read whose SV has reference-allele slots: after the variant alignments
+// (variant tests; a read that passes gets its first reference-allele alignment queued), after that one (the margin
+// test against it can already fail the read, :336-341: then the second reference allele is never aligned) and after the
+// second one.
 __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r)
 {
     const nmsv_read rd = p.reads[r];
     const nmsv_sv sv = p.svs[rd.sv];
     const uint8_t state = p.read_flags[r];        // written only by this read's own chain of continuations
-    const bool stage1 = p.lazy_refs && !(state & kReadVarDone);
-    Sel sl[4];
     bool present[4];
-    bool saturated = false;
+    int lazy_slot[2] = {-1, -1};                  // reference-allele slots that are aligned lazily, in the order they are queued
+    int n_lazy = 0;
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         present[s] = slot_present(sv, s);
+        if (p.lazy_refs && present[s] && is_lazy_slot(sv, s) && alias_of(sv, s) == s) lazy_slot[n_lazy++] = s;
+    }
+    const int n_done = !p.lazy_refs ? 2 : ((state & kReadRef1Done) ? 2 : ((state & kReadVarDone) ? 1 : 0));   // lazy results in
+    auto computed = [&](int s) {                  // is the alignment of slot s available now?
+        if (!p.lazy_refs || !is_lazy_slot(sv, s)) return true;
+        const int a = alias_of(sv, s);
+        return (a == lazy_slot[0] && n_done >= 1) || (a == lazy_slot[1] && n_done >= 2);
+    };
+    Sel sl[4];
+    bool have[4];
+    bool saturated = false;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
         Sel x = {0, 0, 0, 0};
-        if (present[s] && !(stage1 && is_lazy_slot(sv, s))) {
+        have[s] = present[s] && computed(s);
+        if (have[s]) {
             x = select_strand(p.fwd + r * 4u + (uint32_t)alias_of(sv, s));
             saturated |= x.score < 0;
         }
@@ -775,36 +791,32 @@ __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r
         else pass |= (m - sl[v].erow <= sv.qstart_max[v]);                       // qstart = m - read_end1_r
     }
     pass = pass && mapq_ok(sv, rd);
-    if (stage1) {
-        if (!pass) { p.read_flags[r] = 0; return; }
-        uint32_t n = 0;
-        for (int s = NMSV_SLOT_REF1; s <= NMSV_SLOT_REF2; ++s)
-            n += (present[s] && alias_of(sv, s) == s && p.lens[rd.seq]) ? 1u : 0u;
-        if (n) {
-            p.read_flags[r] = kReadVarDone;
-            p.group_remaining[r] = n;          // published with the tasks (fence inside push_task)
-            atomicAdd(&p.cells[kTasksSpawnedFwd], (unsigned long long)n);
+    // margin test (:336-341, :384-385) against the reference alleles that are known so far: some variant segment must
+    // beat every one of them by the margin. With all of them known this is the reference's test.
+    const bool needs_margin = sbnd || (sv.flags & NMSV_SV_SHORT_DEL_DUP);
+    if (pass && needs_margin) {
+        bool any = false;
+        for (int v = 0; v < nvar; ++v) {
+            bool ok = present[v];
             for (int s = NMSV_SLOT_REF1; s <= NMSV_SLOT_REF2; ++s)
-                if (present[s] && alias_of(sv, s) == s)
-                    push_task(p, make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, p.offsets, p.lens, p.seq_class));
-            return;
+                if (have[s]) ok = ok && sl[v].score >= sl[s].score + sv.margin;
+            any |= ok;
         }
-        // no reference-allele alignment outstanding (no such slot, or they alias variant templates): decide now
-#pragma unroll
-        for (int s = NMSV_SLOT_REF1; s <= NMSV_SLOT_REF2; ++s)
-            if (present[s]) {
-                sl[s] = select_strand(p.fwd + r * 4u + (uint32_t)alias_of(sv, s));
-                p.sel[r * 4u + s] = sl[s];
-            }
+        pass = any;
     }
-    if (sbnd) {
-        pass = pass && present[NMSV_SLOT_REF1] && sl[0].score >= sl[NMSV_SLOT_REF1].score + sv.margin;
-    } else if (sv.flags & NMSV_SV_SHORT_DEL_DUP) {
-        const int r1 = sl[NMSV_SLOT_REF1].score + sv.margin, r2 = sl[NMSV_SLOT_REF2].score + sv.margin;
-        const bool ok1 = present[0] && sl[0].score >= r1 && sl[0].score >= r2;
-        const bool ok2 = present[1] && sl[1].score >= r1 && sl[1].score >= r2;
-        pass = pass && present[NMSV_SLOT_REF1] && present[NMSV_SLOT_REF2] && (ok1 || ok2);
+    if (!pass) { p.read_flags[r] = 0; return; }
+    const int n_avail = n_done < n_lazy ? n_done : n_lazy;
+    if (p.lazy_refs && n_avail < n_lazy && p.lens[rd.seq]) {
+        // still a candidate: its next reference-allele alignment is needed (for the margin test, or just for the record)
+        const int s = lazy_slot[n_avail];
+        p.read_flags[r] = n_avail == 0 ? kReadVarDone : (uint8_t)(kReadVarDone | kReadRef1Done);
+        p.group_remaining[r] = 1u;             // published with the task (fence inside push_task)
+        atomicAdd(&p.cells[kTasksSpawnedFwd], 1ull);
+        push_task(p, make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, p.offsets, p.lens, p.seq_class));
+        return;
     }
+    if (sbnd) pass = present[NMSV_SLOT_REF1];
+    else if (sv.flags & NMSV_SV_SHORT_DEL_DUP) pass = present[NMSV_SLOT_REF1] && present[NMSV_SLOT_REF2];
     p.read_flags[r] = pass ? kReadCandidate : 0;
     if (!pass) return;
 #pragma unroll
@@ -1251,7 +1263,7 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
                           pl->group_remaining.bytes + pl->rev.bytes + pl->sel.bytes +
                           pl->alns.bytes + pl->flags.bytes + pl->supporting.bytes + pl->records.bytes + pl->bnd.bytes;
     stt.n_classes = (uint32_t)pl->classes.size();
-    stt.kernel_launches = (pl->fused_begin ? 2u + 3 * stt.n_classes : 3u + 2 * stt.n_classes);
+    stt.kernel_launches = (pl->fused_begin ? 2u + 4 * stt.n_classes : 3u + 2 * stt.n_classes);
     // the caller's host buffers may be reused as soon as we return
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     guard.p = nullptr;
@@ -1334,13 +1346,13 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     }
 
     if (pl->fused_begin) {
-        // What is still queued: tasks whose class had its launch before they were queued. A chain is at most three
-        // tasks deep (variant -> reference allele -> begin pass) and all variant tasks are done by now, so after the
-        // first round every reference-allele task is done and after the second every begin task. Each launch drains its
+        // What is still queued: tasks whose class had its launch before they were queued. A chain is at most four
+        // tasks deep (variant -> first reference allele -> second -> begin pass) and all variant tasks are done by now,
+        // so after the first two rounds every reference-allele task is done and after the third every begin task. Each launch drains its
         // queue as a dynamic one (a continuation may append to the queue of the running launch); normally these launches
         // find nothing (a few microseconds each).
         sp.tasks = nullptr; sp.n_tasks_dev = nullptr; sp.n_tasks = 0;
-        for (int round = 0; round < 2; ++round)
+        for (int round = 0; round < 3; ++round)
             for (size_t i = 0; i < pl->classes.size(); ++i) {
                 sp.queue_head = pl->counters.as<uint32_t>() + kCntFwdQueue + i;
                 set_dyn(i);
