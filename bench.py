@@ -276,7 +276,7 @@ def stage_seam_e2e(eng, wl, order, n_cand, checked, supporting, n_records) -> di
                     C.BATCH_BASES, C.INFLIGHT = mb << 20, fl
                     run()
                     sweep[f"{mb}MB x{fl}"] = n_cand / min(run(), run())
-            C.INFLIGHT = 3
+            C.INFLIGHT = 4
             C.BATCH_BASES = default
             log("[stage seam] candidates/s by batch size:", {k: round(v) for k, v in sweep.items()})
         got_c, got_s, n_info = [], [], 0

@@ -35,13 +35,14 @@ from .engine import DEFAULT_SCORING, AsciiSlice, Engine, SeqPack, default_engine
 from .my_seq import needs_explicit_revcomp, reverse_complement
 
 # maximum number of read bases packed into one device batch (host memory / H2D granularity, not a GPU limit)
-# Measured on the bench's seam files (one Python process, one B200, candidates/s through count_sread_from_seam):
-# 8 MB 615, 16 MB 941, 32 MB 1034, 64 MB 818, 160 MB 821 -- small enough that parsing batch k+1 hides behind the GPU
-# work of batch k, large enough that a launch is not all tail.
-BATCH_BASES = int(os.environ.get("NMSV_BATCH_BASES", str(32 << 20)))
+# Measured on the bench's seam files (one Python process, one B200, candidates/s through count_sread_from_seam, batch
+# size x calls in flight): 16 MB x2 932, 32 MB x2 1131, 64 MB x2 1244, 16 MB x3 1238, 32 MB x3 1260, 64 MB x3 1258,
+# 16 MB x4 1308, 32 MB x4 1364, 64 MB x4 1415 (device resident: 1644) -- the host is ahead of the GPU, what counts is that
+# a launch is not all tail and that the end of one launch is filled by the next.
+BATCH_BASES = int(os.environ.get("NMSV_BATCH_BASES", str(64 << 20)))
 # GPU calls in flight per Alignment_counter (each on a context of its own): the end of a launch runs at low occupancy,
 # the next calls fill it
-INFLIGHT = int(os.environ.get("NMSV_STAGE_INFLIGHT", "3"))
+INFLIGHT = int(os.environ.get("NMSV_STAGE_INFLIGHT", "4"))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -584,20 +585,36 @@ class Alignment_counter(object):
     def _drain_one(self):
         fut, queue, svs = self._pending.pop(0)
         checked, supporting, records = fut.result()       # re-raises an EngineError of the worker
+        # plain Python ints in three bulk conversions (per-record numpy scalar access is ~20 us per record)
+        n_rec = len(records)
+        rec_sv = records["sv"].tolist()
+        rec_read = records["read"].tolist()
+        rec_aln = np.ascontiguousarray(records["aln"]).view(np.int32).reshape(n_rec, 24).tolist() if n_rec else []
+        begin = svs["read_begin"].tolist()
+        checked_l, supporting_l = checked.tolist(), supporting.tolist()
         by_sv: Dict[int, list] = {}
-        for rec in records:
-            by_sv.setdefault(int(rec["sv"]), []).append(rec)
+        for k in range(n_rec):
+            by_sv.setdefault(rec_sv[k], []).append(k)
+        none12 = "\t".join(["None"] * 12)
+        count_lines, info_lines = [], []
+
+        def six(a, o):        # one entry of the dict of ssw_check (:162): score, qstart, qend, tstart, tend, strand
+            return f"{a[o]}\t{a[o + 1]}\t{a[o + 2]}\t{a[o + 3]}\t{a[o + 4]}\t{'+' if a[o + 5] > 0 else '-'}"
         for i, job in enumerate(queue):
-            head = "\t".join(job.key.split(","))
-            print(f"{head}\t{int(checked[i])}\t{int(supporting[i])}", file=self.hout_count)
-            for rec in by_sv.get(i, []):
-                rid = job.read_id(int(rec["read"]) - int(svs[i]["read_begin"]))
+            head = job.key.replace(",", "\t")
+            count_lines.append(f"{head}\t{checked_l[i]}\t{supporting_l[i]}\n")
+            for k in by_sv.get(i, ()):
+                a = rec_aln[k]
+                rid = job.read_id(rec_read[k] - begin[i])
                 if job.is_sbnd:
-                    fields = _aln_list(rec["aln"][0])
+                    tail = six(a, 0)
+                elif job.short:
+                    tail = f"{six(a, 0)}\t{six(a, 6)}\t{six(a, 12)}\t{six(a, 18)}"
                 else:
-                    fields = _aln_list(rec["aln"][0]) + _aln_list(rec["aln"][1])
-                    fields += (_aln_list(rec["aln"][2]) + _aln_list(rec["aln"][3])) if job.short else ["None"] * 12
-                print(f"{head}\t{rid}\t" + "\t".join(str(x) for x in fields), file=self.hout_ainfo)
+                    tail = f"{six(a, 0)}\t{six(a, 6)}\t{none12}"
+                info_lines.append(f"{head}\t{rid}\t{tail}\n")
+        self.hout_count.write("".join(count_lines))
+        self.hout_ainfo.write("".join(info_lines))
 
     def close(self):
         self.flush()
