@@ -584,7 +584,9 @@ enum : uint32_t { kCellsFwd = 0, kCellsBegin = 1, kTasksSpawnedFwd = 2, kCellsTo
 enum : uint8_t { kReadCandidate = 1, kReadSupporting = 2,
                  kReadPruned = 4,      // mapq test already failed: counted as checked, never aligned (:344-346, :388-389)
                  kReadVarDone = 8,     // lazy reference alleles: the variant tests passed, the first reference allele is queued
-                 kReadRef1Done = 16 }; // ... the margin test against it passed too, the second one is queued
+                 kReadRef1Done = 16,   // ... the margin test against it passed too, the second one is queued
+                 kReadVarRedo = 32 };  // a variant segment that stayed below its threshold was re-aligned exactly (the read
+                                       // passed through the other segment, so both tuples go into its record)
 
 __device__ __forceinline__ int alias_of(const nmsv_sv& sv, int s)
 {
@@ -615,9 +617,20 @@ __device__ __forceinline__ bool is_lazy_slot(const nmsv_sv& sv, int s)
     return (s == NMSV_SLOT_REF1 || s == NMSV_SLOT_REF2) && alias_of(sv, s) >= NMSV_SLOT_REF1;
 }
 
+// Score below which the alignment of variant slot s cannot matter unless another variant segment passes: the score test
+// of the decision rules (:328-333). A task shared by var1 and var2 (identical templates) takes the smaller of the two.
+__device__ __forceinline__ uint32_t var_threshold(const nmsv_sv& sv, int s)
+{
+    if (s > NMSV_SLOT_VAR2) return 0u;
+    int t = sv.score_min[s];
+    const int o = 1 - s;
+    if (!(sv.flags & NMSV_SV_SBND) && sv.tmpl[o] == sv.tmpl[s] && sv.tmpl_rc[o] == sv.tmpl_rc[s] && sv.score_min[o] < t) t = sv.score_min[o];
+    return t > 1 ? (uint32_t)t : 0u;
+}
+
 __device__ __forceinline__ SwTask make_fwd_task(const nmsv_sv& sv, int s, uint32_t out, uint32_t read_seq,
                                                 const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ lens,
-                                                const uint8_t* __restrict__ seq_class)
+                                                const uint8_t* __restrict__ seq_class, uint32_t thr = 0u)
 {
     SwTask t;
     memset(&t, 0, sizeof(t));
@@ -633,6 +646,7 @@ __device__ __forceinline__ SwTask make_fwd_task(const nmsv_sv& sv, int s, uint32
     t.c_base = offsets[read_seq];
     t.ncols = lens[read_seq];
     t.rclass = (uint32_t)seq_class[tm];   // strip height R itself
+    t.thr = thr;
     return t;
 }
 
@@ -656,7 +670,8 @@ __global__ void plan_fwd_kernel(const nmsv_sv* __restrict__ svs, const nmsv_read
     const bool pruned = prune && !mapq_ok(sv, rd);
     if (pruned && s == 0) read_flags[r] = kReadPruned;       // zeroed before the launch
     if (!pruned && slot_present(sv, s) && alias_of(sv, s) == s && !(lazy_refs && is_lazy_slot(sv, s))) {
-        t = make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, offsets, lens, seq_class);
+        // with the continuation chain available, variant alignments are speculative: exact only from the score test up
+        t = make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, offsets, lens, seq_class, lazy_refs ? var_threshold(sv, s) : 0u);
         if (t.ncols) atomicAdd(&group_remaining[r], 1u);      // zeroed before the launch
     }
     tasks[i] = t;
@@ -769,13 +784,20 @@ __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r
     Sel sl[4];
     bool have[4];
     bool saturated = false;
+    int inexact = -1;                             // a variant slot with a task of its own whose result is only "below threshold"
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
         Sel x = {0, 0, 0, 0};
         have[s] = present[s] && computed(s);
         if (have[s]) {
-            x = select_strand(p.fwd + r * 4u + (uint32_t)alias_of(sv, s));
+            const int a = alias_of(sv, s);
+            x = select_strand(p.fwd + r * 4u + (uint32_t)a);
             saturated |= x.score < 0;
+            if (p.lazy_refs && !(state & kReadVarRedo) && s <= NMSV_SLOT_VAR2 && x.score >= 0 &&
+                (uint32_t)x.score < var_threshold(sv, a)) {
+                x.strand = 0;                     // not an alignment: the speculative task only says "below the threshold"
+                if (a == s) inexact = s;
+            }
         }
         sl[s] = x;
         p.sel[r * 4u + s] = x;
@@ -805,11 +827,20 @@ __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r
         pass = any;
     }
     if (!pass) { p.read_flags[r] = 0; return; }
+    if (inexact >= 0 && p.lens[rd.seq]) {
+        // The read passes through the other variant segment, so the record will hold this segment's tuple too: align it
+        // again, exactly. (Both segments below their thresholds never get here; a passing segment is exact.)
+        p.read_flags[r] = (uint8_t)(state | kReadVarRedo);
+        p.group_remaining[r] = 1u;
+        atomicAdd(&p.cells[kTasksSpawnedFwd], 1ull);
+        push_task(p, make_fwd_task(sv, inexact, r * 4u + (uint32_t)inexact, rd.seq, p.offsets, p.lens, p.seq_class));
+        return;
+    }
     const int n_avail = n_done < n_lazy ? n_done : n_lazy;
     if (p.lazy_refs && n_avail < n_lazy && p.lens[rd.seq]) {
         // still a candidate: its next reference-allele alignment is needed (for the margin test, or just for the record)
         const int s = lazy_slot[n_avail];
-        p.read_flags[r] = n_avail == 0 ? kReadVarDone : (uint8_t)(kReadVarDone | kReadRef1Done);
+        p.read_flags[r] = (uint8_t)((state & kReadVarRedo) | (n_avail == 0 ? kReadVarDone : (kReadVarDone | kReadRef1Done)));
         p.group_remaining[r] = 1u;             // published with the task (fence inside push_task)
         atomicAdd(&p.cells[kTasksSpawnedFwd], 1ull);
         push_task(p, make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, p.offsets, p.lens, p.seq_class));
@@ -1263,7 +1294,7 @@ extern "C" int nmsv_plan_create(nmsv_ctx* ctx, nmsv_plan** out, const uint8_t* c
                           pl->group_remaining.bytes + pl->rev.bytes + pl->sel.bytes +
                           pl->alns.bytes + pl->flags.bytes + pl->supporting.bytes + pl->records.bytes + pl->bnd.bytes;
     stt.n_classes = (uint32_t)pl->classes.size();
-    stt.kernel_launches = (pl->fused_begin ? 2u + 4 * stt.n_classes : 3u + 2 * stt.n_classes);
+    stt.kernel_launches = (pl->fused_begin ? 2u + 5 * stt.n_classes : 3u + 2 * stt.n_classes);
     // the caller's host buffers may be reused as soon as we return
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
     guard.p = nullptr;
@@ -1346,13 +1377,13 @@ extern "C" int nmsv_plan_run(nmsv_plan* pl)
     }
 
     if (pl->fused_begin) {
-        // What is still queued: tasks whose class had its launch before they were queued. A chain is at most four
-        // tasks deep (variant -> first reference allele -> second -> begin pass) and all variant tasks are done by now,
-        // so after the first two rounds every reference-allele task is done and after the third every begin task. Each launch drains its
+        // What is still queued: tasks whose class had its launch before they were queued. A chain is at most five
+        // tasks deep (variant -> exact redo of the other variant segment -> first reference allele -> second -> begin
+        // pass) and all speculative variant tasks are done by now, so four rounds see every task done. Each launch drains its
         // queue as a dynamic one (a continuation may append to the queue of the running launch); normally these launches
         // find nothing (a few microseconds each).
         sp.tasks = nullptr; sp.n_tasks_dev = nullptr; sp.n_tasks = 0;
-        for (int round = 0; round < 3; ++round)
+        for (int round = 0; round < 4; ++round)
             for (size_t i = 0; i < pl->classes.size(); ++i) {
                 sp.queue_head = pl->counters.as<uint32_t>() + kCntFwdQueue + i;
                 set_dyn(i);

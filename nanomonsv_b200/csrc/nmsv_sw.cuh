@@ -94,7 +94,10 @@ struct SwTask {          // 64 bytes
                          // The running maximum then starts at best0 - 1, so that only the cells that reach best0 --
                          // the candidates for the begin cell -- take the exact path instead of every cell of the
                          // climb along the alignment.
-    uint32_t pad_[3];
+    uint32_t thr;        // forward task: only scores >= thr have to be exact (0 = all). The running maxima of both halves
+                         // start at thr - 1: a half that never reaches thr reports thr - 1 with meaningless coordinates,
+                         // and none of its cells takes the exact path of the position tracking.
+    uint32_t pad_[2];
 };
 
 static_assert(sizeof(SwTask) == 64, "the dynamic queue reads a task as four 16-byte words");
@@ -377,7 +380,7 @@ __device__ __forceinline__ bool pick_task(const SwParams& p, uint32_t n_tasks, S
     const uint4 w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2), w3 = __ldcg(q + 3);
     task.a_base = ((uint64_t)w0.y << 32) | w0.x; task.b_base = ((uint64_t)w0.w << 32) | w0.z;
     task.c_base = ((uint64_t)w1.y << 32) | w1.x; task.a_len = w1.z; task.b_len = w1.w;
-    task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w; task.best0 = w3.x;
+    task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w; task.best0 = w3.x; task.thr = w3.y;
     return true;
 }
 
@@ -396,7 +399,7 @@ __device__ __noinline__ uint32_t claim_job(BlockCtl* ctl, const SwParams& p, uin
         else {
             if (ctl->cur == (uint32_t)kSlots) {
                 SwTask task;
-                task.pad_[0] = task.pad_[1] = task.pad_[2] = 0;
+                task.pad_[0] = task.pad_[1] = 0;
                 if (pick_task(p, n_tasks, task)) {
                     if (task.rclass == R && task.ncols != 0) {
                         const uint32_t si = (uint32_t)__ffs((int)~ctl->slot_busy) - 1u;      // a free slot exists (kSlots > kW)
@@ -408,7 +411,7 @@ __device__ __noinline__ uint32_t claim_job(BlockCtl* ctl, const SwParams& p, uin
                         s.next_tile = 0; s.tiles_done = 0; s.sat = 0;
                         // begin pass: the score is known (only cells that reach it matter); its unused half B holds the
                         // floor everywhere, park its bound out of reach so that it never takes the exact path
-                        s.lb[0] = task.best0; s.lb[1] = task.b_len ? 0u : 256u;
+                        s.lb[0] = task.best0 > task.thr ? task.best0 : task.thr; s.lb[1] = task.b_len ? task.thr : 256u;
                         s.best_s[0] = (int32_t)task.best0; s.best_c[0] = task.best0 ? 0x7fffffff : 0;
                         s.best_r[0] = task.best0 ? 0x7fffffff : (int32_t)task.a_len - 1;
                         s.best_s[1] = 0; s.best_c[1] = 0; s.best_r[1] = (int32_t)task.b_len - 1;

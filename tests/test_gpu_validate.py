@@ -232,7 +232,7 @@ def test_fused_and_separate_begin_pass_agree(engine, monkeypatch):
                 checked, supporting, records = plan.download()
                 alns, flags = plan.download_alns()
                 st = plan.stats()
-                assert st["kernel_launches"] == (2 + 4 * st["n_classes"] if mode == "1" else 3 + 2 * st["n_classes"])
+                assert st["kernel_launches"] == (2 + 5 * st["n_classes"] if mode == "1" else 3 + 2 * st["n_classes"])
                 out[mode, prune] = (checked, supporting, records, alns, flags, st["rev_tasks"])
                 plan.close()
         a, b = out["1", False], out["0", False]
