@@ -630,7 +630,7 @@ __device__ __forceinline__ uint32_t var_threshold(const nmsv_sv& sv, int s)
 
 __device__ __forceinline__ SwTask make_fwd_task(const nmsv_sv& sv, int s, uint32_t out, uint32_t read_seq,
                                                 const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ lens,
-                                                const uint8_t* __restrict__ seq_class, uint32_t thr = 0u)
+                                                const uint8_t* __restrict__ seq_class, uint32_t thr = 0u, uint32_t hi = 0u)
 {
     SwTask t;
     memset(&t, 0, sizeof(t));
@@ -647,6 +647,7 @@ __device__ __forceinline__ SwTask make_fwd_task(const nmsv_sv& sv, int s, uint32
     t.ncols = lens[read_seq];
     t.rclass = (uint32_t)seq_class[tm];   // strip height R itself
     t.thr = thr;
+    t.hi = hi;
     return t;
 }
 
@@ -806,6 +807,15 @@ __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r
     const bool sbnd = sv.flags & NMSV_SV_SBND;
     bool pass = false;
     const int nvar = sbnd ? 1 : 2;
+    const bool needs_margin = sbnd || (sv.flags & NMSV_SV_SHORT_DEL_DUP);
+    // a lazily aligned reference allele was abandoned at (best variant score - margin + 1): such a result only says "within
+    // the margin", it is not an alignment (the read fails the margin test below)
+    if (p.lazy_refs && needs_margin) {
+        int best_var = 0;
+        for (int v = 0; v < nvar; ++v) if (present[v] && sl[v].score > best_var) best_var = sl[v].score;
+        for (int s = NMSV_SLOT_REF1; s <= NMSV_SLOT_REF2; ++s)
+            if (have[s] && is_lazy_slot(sv, s) && sl[s].score >= best_var - sv.margin + 1) { sl[s].strand = 0; p.sel[r * 4u + s].strand = 0; }
+    }
     for (int v = 0; v < nvar; ++v) {
         if (!present[v] || sl[v].score < sv.score_min[v]) continue;
         const int m = (int)p.lens[sv.tmpl[v]];
@@ -815,7 +825,6 @@ __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r
     pass = pass && mapq_ok(sv, rd);
     // margin test (:336-341, :384-385) against the reference alleles that are known so far: some variant segment must
     // beat every one of them by the margin. With all of them known this is the reference's test.
-    const bool needs_margin = sbnd || (sv.flags & NMSV_SV_SHORT_DEL_DUP);
     if (pass && needs_margin) {
         bool any = false;
         for (int v = 0; v < nvar; ++v) {
@@ -840,10 +849,21 @@ __device__ __noinline__ void decide_read(const DecideParams& p, const uint32_t r
     if (p.lazy_refs && n_avail < n_lazy && p.lens[rd.seq]) {
         // still a candidate: its next reference-allele alignment is needed (for the margin test, or just for the record)
         const int s = lazy_slot[n_avail];
+        // Where the margin test applies, all that matters about a reference allele is whether it scores within the
+        // margin of the best variant segment: some segment beats it iff its score is below max_v(score_v) - margin + 1.
+        // The task is abandoned as soon as a cell reaches that value (the read fails, nothing of it is recorded).
+        uint32_t hi = 0u;
+        if (needs_margin) {
+            int best_var = 0;
+            for (int v = 0; v < nvar; ++v) if (present[v] && sl[v].score > best_var) best_var = sl[v].score;
+            const int b = best_var - sv.margin + 1;
+            if (b <= 0) { p.read_flags[r] = 0; return; }      // every reference-allele score fails the margin test
+            hi = (uint32_t)b;
+        }
         p.read_flags[r] = (uint8_t)((state & kReadVarRedo) | (n_avail == 0 ? kReadVarDone : (kReadVarDone | kReadRef1Done)));
         p.group_remaining[r] = 1u;             // published with the task (fence inside push_task)
         atomicAdd(&p.cells[kTasksSpawnedFwd], 1ull);
-        push_task(p, make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, p.offsets, p.lens, p.seq_class));
+        push_task(p, make_fwd_task(sv, s, r * 4u + (uint32_t)s, rd.seq, p.offsets, p.lens, p.seq_class, 0u, hi));
         return;
     }
     if (sbnd) pass = present[NMSV_SLOT_REF1];

@@ -97,7 +97,10 @@ struct SwTask {          // 64 bytes
     uint32_t thr;        // forward task: only scores >= thr have to be exact (0 = all). The running maxima of both halves
                          // start at thr - 1: a half that never reaches thr reports thr - 1 with meaningless coordinates,
                          // and none of its cells takes the exact path of the position tracking.
-    uint32_t pad_[2];
+    uint32_t hi;         // forward task: abandon the task as soon as a score reaches hi (0 = never): the caller only needs to
+                         // know THAT it does (a reference allele that scores within the margin of the variant, :336-341);
+                         // the result then reads score = hi for both halves, coordinates meaningless.
+    uint32_t pad_[1];
 };
 
 static_assert(sizeof(SwTask) == 64, "the dynamic queue reads a task as four 16-byte words");
@@ -172,12 +175,13 @@ struct alignas(16) Slot {              // one task in flight in this block (the 
     uint32_t lb[2];                    // per half: a score some cell of the task is known to reach (lower bound of the result)
     int32_t best_s[2], best_c[2], best_r[2];
     uint32_t last_out;                 // out-link of the tile claimed last = in-link of the next one
-    uint32_t pad_;
+    uint32_t abort;                    // a tile saw a score >= task.hi: every tile of the task stops at its next chunk
+    unsigned long long cells_done;     // cells the tiles of the task actually computed
 };
 
 // columns [0, produced) written (whole-read buffers only) / [0, consumed) no longer needed; base = position of the
 // link's column 0 in the ring's stream
-struct LinkCtl { uint32_t produced, consumed, base, pad_; };
+struct LinkCtl { uint32_t produced, consumed, base, users; };      // users: ends of the link (producer, consumer) not yet finished
 
 struct BlockCtl {
     uint32_t lock, quit, n_waiting, cur;             // cur = slot whose tiles are being dealt out (kSlots = none)
@@ -300,10 +304,11 @@ __device__ __forceinline__ unsigned long long global_ns()
 // return of the C ABI instead of a hung device.
 constexpr unsigned long long kWatchdogNs = 20ull * 1000 * 1000 * 1000;
 
-__device__ __noinline__ void link_wait_slow(const uint32_t* flag, uint32_t need)
+__device__ __noinline__ void link_wait_slow(const uint32_t* flag, uint32_t need, const uint32_t* abort)
 {
     const unsigned long long t0 = global_ns();
-    while ((int32_t)(ld_vol(flag) - need) < 0) {
+    // warp-uniform exit (votes); an abandoned task ends the wait: the other side may be gone
+    while (__any_sync(kFull, (int32_t)(ld_vol(flag) - need) < 0) && !__any_sync(kFull, ld_vol(abort) != 0u)) {
         __nanosleep(40);
         if (global_ns() - t0 > kWatchdogNs) __trap();
     }
@@ -312,18 +317,18 @@ __device__ __noinline__ void link_wait_slow(const uint32_t* flag, uint32_t need)
 // wait until *flag >= need (a column count written by another warp of this block). The common case -- the other side
 // is far enough along -- is one shared-memory load and a vote; the poll loop is kept out of line (a data-dependent
 // loop inlined into the kernel body costs the compiler its convergence analysis of the hot loop).
-__device__ __forceinline__ void link_wait(const uint32_t* flag, uint32_t need)
+__device__ __forceinline__ void link_wait(const uint32_t* flag, uint32_t need, const uint32_t* abort)
 {
-    if (__any_sync(kFull, (int32_t)(ld_vol(flag) - need) < 0)) link_wait_slow(flag, need);
+    if (__any_sync(kFull, (int32_t)(ld_vol(flag) - need) < 0)) link_wait_slow(flag, need, abort);
     __threadfence_block();
 }
 
 // some ring entry of the warp is not yet written in this lap: poll (out of line, like every data-dependent loop, and
 // called by the whole warp so that the call site stays convergent; lanes with stale = false return at once)
-__device__ __noinline__ uint2 ring_poll(const uint2* ptr, uint32_t tag, uint2 v, bool stale)
+__device__ __noinline__ uint2 ring_poll(const uint2* ptr, uint32_t tag, uint2 v, bool stale, const uint32_t* abort)
 {
     const unsigned long long t0 = global_ns();
-    while (__any_sync(kFull, stale)) {        // warp-uniform exit
+    while (__any_sync(kFull, stale) && !__any_sync(kFull, ld_vol(abort) != 0u)) {        // warp-uniform exit
         __nanosleep(100);
         if (stale) {
             v = __ldcg(ptr);
@@ -380,7 +385,7 @@ __device__ __forceinline__ bool pick_task(const SwParams& p, uint32_t n_tasks, S
     const uint4 w0 = __ldcg(q), w1 = __ldcg(q + 1), w2 = __ldcg(q + 2), w3 = __ldcg(q + 3);
     task.a_base = ((uint64_t)w0.y << 32) | w0.x; task.b_base = ((uint64_t)w0.w << 32) | w0.z;
     task.c_base = ((uint64_t)w1.y << 32) | w1.x; task.a_len = w1.z; task.b_len = w1.w;
-    task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w; task.best0 = w3.x; task.thr = w3.y;
+    task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w; task.best0 = w3.x; task.thr = w3.y; task.hi = w3.z;
     return true;
 }
 
@@ -399,7 +404,7 @@ __device__ __noinline__ uint32_t claim_job(BlockCtl* ctl, const SwParams& p, uin
         else {
             if (ctl->cur == (uint32_t)kSlots) {
                 SwTask task;
-                task.pad_[0] = task.pad_[1] = 0;
+                task.pad_[0] = 0;
                 if (pick_task(p, n_tasks, task)) {
                     if (task.rclass == R && task.ncols != 0) {
                         const uint32_t si = (uint32_t)__ffs((int)~ctl->slot_busy) - 1u;      // a free slot exists (kSlots > kW)
@@ -408,7 +413,7 @@ __device__ __noinline__ uint32_t claim_job(BlockCtl* ctl, const SwParams& p, uin
                         s.task = task;
                         const uint32_t rows = task.a_len > task.b_len ? task.a_len : task.b_len;
                         s.ntiles = (rows + 32u * R - 1u) / (32u * R);
-                        s.next_tile = 0; s.tiles_done = 0; s.sat = 0;
+                        s.next_tile = 0; s.tiles_done = 0; s.sat = 0; s.abort = 0; s.cells_done = 0;
                         // begin pass: the score is known (only cells that reach it matter); its unused half B holds the
                         // floor everywhere, park its bound out of reach so that it never takes the exact path
                         s.lb[0] = task.best0 > task.thr ? task.best0 : task.thr; s.lb[1] = task.b_len ? task.thr : 256u;
@@ -440,14 +445,17 @@ __device__ __noinline__ uint32_t claim_job(BlockCtl* ctl, const SwParams& p, uin
                         if (freeg) { out = (uint32_t)kRings + (uint32_t)__ffs((int)freeg) - 1u; ctl->gbuf_busy |= 1u << (out - kRings); }
                         else ok = false;                                 // both in use: their consumers are running, retry
                     } else {
-                        out = (uint32_t)__ffs((int)~ctl->ring_busy) - 1u;    // a free ring exists (kRings = kW + 1)
-                        ctl->ring_busy |= 1u << out;
+                        // kRings = kW + 1 rings cover every link with a running end in normal operation; while abandoned
+                        // tasks wind down (a consumer gone, its producer still on its last chunk) there can be more: retry
+                        const uint32_t freer = ~ctl->ring_busy;
+                        if (freer) { out = (uint32_t)__ffs((int)freer) - 1u; ctl->ring_busy |= 1u << out; }
+                        else ok = false;
                     }
                 }
                 if (ok) {
                     ret = ctl->cur | (j << 4) | (s.last_out << 24) | (out << 28);
                     if (out != kNoLink) {
-                        ctl->links[out].produced = 0u; ctl->links[out].consumed = 0u;
+                        ctl->links[out].produced = 0u; ctl->links[out].consumed = 0u; ctl->links[out].users = 2u;
                         ctl->links[out].base = ctl->stream[out];
                         ctl->stream[out] += s.task.ncols;
                     }
@@ -476,13 +484,36 @@ __device__ __noinline__ void sw_task_done(const GroupHook* hook, uint32_t* group
     }
 }
 
+// An abandoned task (Slot::abort): the producer of a link still owes the ring the rest of the link's stream positions --
+// every ring entry has to be written once per lap, with the parity of its lap, or a later link would take a stale entry
+// for a fresh one. Only the last lap of the range decides what the entries hold in the end. Whole-read buffers just
+// publish the full count. The consumer is abandoning the task too and ignores what it reads.
+__device__ __noinline__ void link_abort_fill(const SwParams& p, uint2* base, uint32_t mask, bool ring, uint32_t q0, int from_col,
+                                             int ncols, LinkCtl* link)
+{
+    const int lane = threadIdx.x & 31;
+    if (ring) {
+        int first = ncols - (int)p.ring_cols;
+        if (first < from_col) first = from_col;
+        for (int col = first + lane; col < ncols; col += 32) {
+            const uint32_t q = q0 + (uint32_t)col;
+            __stcg(base + (q & mask), make_uint2((((q >> p.ring_shift) + 1u) & 1u) << 15, 0u));
+        }
+    } else {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&link->produced) = (uint32_t)ncols;
+    }
+    __syncwarp();
+}
+
 // lane 0, at the end of a tile: merge the tile's best cells into the task's result (higher score, then smaller column,
 // then smaller row -- parasail's end cell), release the tile's in-link, and when this was the task's last tile to finish
 // store the result and run the continuation.
 __device__ __noinline__ void finish_job(BlockCtl* ctl, const SwParams& p, uint32_t code, int s0, int c0, int r0,
-                                        int s1, int c1, int r1, uint32_t sat)
+                                        int s1, int c1, int r1, uint32_t sat, unsigned long long cells_done)
 {
-    const uint32_t si = code & 15u, in_link = (code >> 24) & 15u;
+    const uint32_t si = code & 15u, in_link = (code >> 24) & 15u, out_link = code >> 28;
     Slot& s = ctl->slots[si];
     ctl_lock(ctl);
     if (s0 > 0 && (s0 > s.best_s[0] || (s0 == s.best_s[0] && (c0 < s.best_c[0] || (c0 == s.best_c[0] && r0 < s.best_r[0]))))) {
@@ -492,9 +523,16 @@ __device__ __noinline__ void finish_job(BlockCtl* ctl, const SwParams& p, uint32
         s.best_s[1] = s1; s.best_c[1] = c1; s.best_r[1] = r1;
     }
     s.sat |= sat;
-    if (in_link != kNoLink) {
-        if (in_link < (uint32_t)kRings) ctl->ring_busy &= ~(1u << in_link);
-        else ctl->gbuf_busy &= ~(1u << (in_link - (uint32_t)kRings));
+    s.cells_done += cells_done;
+    // a link is handed out again when both of its ends are done with it (the producer of an abandoned task may still be
+    // filling the ring when its consumer has already left)
+    for (int e = 0; e < 2; ++e) {
+        const uint32_t l = e ? out_link : in_link;
+        if (l == kNoLink) continue;
+        if (--ctl->links[l].users == 0u) {
+            if (l < (uint32_t)kRings) ctl->ring_busy &= ~(1u << l);
+            else ctl->gbuf_busy &= ~(1u << (l - (uint32_t)kRings));
+        }
     }
     s.tiles_done += 1u;
     const bool done = s.tiles_done == s.ntiles;
@@ -504,8 +542,12 @@ __device__ __noinline__ void finish_job(BlockCtl* ctl, const SwParams& p, uint32
     if (done) {
         res.score[0] = (s.sat & 1u) ? -1 : s.best_s[0]; res.row[0] = s.best_r[0]; res.col[0] = s.best_c[0];
         res.score[1] = s.task.b_len ? ((s.sat & 2u) ? -1 : s.best_s[1]) : 0; res.row[1] = s.best_r[1]; res.col[1] = s.best_c[1];
+        if (s.abort) {       // abandoned: all the caller learns is that a score reaches hi
+            res.score[0] = (int32_t)s.task.hi; res.score[1] = s.task.b_len ? (int32_t)s.task.hi : 0;
+            res.row[0] = res.row[1] = res.col[0] = res.col[1] = 0;
+        }
         out = s.task.out; flags = s.task.flags;
-        cells = (unsigned long long)(s.task.a_len + s.task.b_len) * (unsigned long long)s.task.ncols;
+        cells = s.cells_done;
         ctl->slot_busy &= ~(1u << si);
     }
     ctl_unlock(ctl);
@@ -597,6 +639,7 @@ sw_wavefront_kernel(const SwParams p)
             task.a_base = ((uint64_t)w0.y << 32) | w0.x; task.b_base = ((uint64_t)w0.w << 32) | w0.z;
             task.c_base = ((uint64_t)w1.y << 32) | w1.x; task.a_len = w1.z; task.b_len = w1.w;
             task.ncols = w2.x; task.flags = w2.y; task.out = w2.z; task.rclass = w2.w;
+            task.hi = reinterpret_cast<const uint32_t*>(&slot->task.hi)[0];
         }
 
         const int a_len = (int)task.a_len, b_len = (int)task.b_len, ncols = (int)task.ncols;
@@ -613,6 +656,8 @@ sw_wavefront_kernel(const SwParams p)
         // run-time saturation watch (only tasks whose bound exceeds the cap can trip it)
         const uint32_t sat_thr = hbound <= hcap ? 0xffffu : (uint32_t)(hcap - 32 * p.match);
         uint32_t sat = 0;          // bit h: half h came within 32 steps of the cap
+        const uint32_t hi = task.hi;          // abandon the task when a score reaches hi (0: never)
+        int cols_done = ncols;                // columns this tile went through (fewer when the task was abandoned)
 
         {
             const int row0 = tile * 32 * R + lane * R;
@@ -798,7 +843,7 @@ sw_wavefront_kernel(const SwParams p)
                 //      tile above, from its link once the producer has published them)
                 __syncwarp();
                 const bool prefetched = tma_task && t0 >= kChunk && t0 + kChunk <= ncols;   // issued one chunk ago
-                if (has_in && !in_ring) link_wait(&lin->produced, (uint32_t)(t0 + kChunk < ncols ? t0 + kChunk : ncols));
+                if (has_in && !in_ring) link_wait(&lin->produced, (uint32_t)(t0 + kChunk < ncols ? t0 + kChunk : ncols), &slot->abort);
 #pragma unroll
                 for (int u = 0; u < kChunk / 32; ++u) {
                     const int col = t0 + u * 32 + lane;
@@ -818,7 +863,7 @@ sw_wavefront_kernel(const SwParams p)
                             bv = __ldcg(ptr);
                             stale = in_ring && ((bv.x >> 15) & 1u) != tag;
                         }
-                        if (__any_sync(kFull, stale)) bv = ring_poll(ptr, tag, bv, stale);
+                        if (__any_sync(kFull, stale)) bv = ring_poll(ptr, tag, bv, stale, &slot->abort);
                         if (in_ring) bv.x &= 0xffff7fffu;
                     }
                     // lane 0 consumes entry `col` at step col as (H of row -1 for the next step's diagonal, F entering
@@ -844,6 +889,10 @@ sw_wavefront_kernel(const SwParams p)
                     tma_parity ^= 1u;
                 }
                 __syncwarp();
+                // ---- abandoned task (some tile saw a score >= hi)? No bulk copy is in flight at this point.
+                if (hi) {
+                    if (__any_sync(kFull, ld_vol(&slot->abort) != 0u)) { cols_done = t0 < ncols ? t0 : ncols; break; }
+                }
                 // ---- TMA prefetch of the NEXT chunk of the read into the free ring slot (twice: the ring is mirrored);
                 //      it lands while this chunk is computed. Needs 16-byte aligned addresses and a whole chunk; the
                 //      begin pass (reversed read) and ragged tails use the plain loads above.
@@ -893,6 +942,8 @@ sw_wavefront_kernel(const SwParams p)
                         const uint32_t flg = flb + (uint32_t)(g1 - 1) * p.ext2;
                         const uint32_t tm = wb - flg;
                         sat |= ((tm & 0xffffu) > sat_thr ? 1u : 0u) | ((tm >> 16) > sat_thr ? 2u : 0u);
+                        if (hi && lane == 0 && ((tm & 0xffffu) >= hi || (tm >> 16) >= hi))
+                            *reinterpret_cast<volatile uint32_t*>(&slot->abort) = 1u;
                         // the tiles of the task share what they know: a cell of ANY tile is a lower bound of the result
                         const uint32_t l0 = ld_vol(&slot->lb[0]), l1 = ld_vol(&slot->lb[1]);
                         if (lane == 0) {
@@ -916,7 +967,7 @@ sw_wavefront_kernel(const SwParams p)
                         const int cmax = g1 - 31 < ncols ? (g1 - 31 > 0 ? g1 - 31 : 0) : ncols;
                         if (out_ring) {
                             // a ring holds ring_cols columns: do not overwrite what the consumer has not copied yet
-                            link_wait(&lout->consumed, (uint32_t)cmax > p.ring_cols ? (uint32_t)cmax - p.ring_cols : 0u);
+                            link_wait(&lout->consumed, (uint32_t)cmax > p.ring_cols ? (uint32_t)cmax - p.ring_cols : 0u, &slot->abort);
                         } else {
                             __threadfence();
                             __syncwarp();
@@ -935,7 +986,9 @@ sw_wavefront_kernel(const SwParams p)
                 }
             }
 
-            if (has_out && !out_ring) {          // the last group's stores, then the final count
+            if (cols_done < ncols) {             // abandoned before the end
+                if (has_out) link_abort_fill(p, b_out, m_out, out_ring, q_out, cols_done - 31 > 0 ? cols_done - 31 : 0, ncols, lout);
+            } else if (has_out && !out_ring) {   // the last group's stores, then the final count
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) *reinterpret_cast<volatile uint32_t*>(&lout->produced) = (uint32_t)ncols;
@@ -954,7 +1007,11 @@ sw_wavefront_kernel(const SwParams p)
             resolve_snap(1, c1, r1);
             if (s1 <= 0) { s1 = 0; c1 = 0x7fffffff; r1 = 0x7fffffff; }
             warp_argbest(s1, c1, r1);
-            if (lane == 0) finish_job(ctl, p, code, s0, c0, r0, s1, c1, r1, sat);
+            if (lane == 0) {
+                const int ra = a_len - tile * 32 * R, rb = b_len - tile * 32 * R;
+                const int rows_here = (ra < 0 ? 0 : (ra > 32 * R ? 32 * R : ra)) + (rb < 0 ? 0 : (rb > 32 * R ? 32 * R : rb));
+                finish_job(ctl, p, code, s0, c0, r0, s1, c1, r1, sat, (unsigned long long)rows_here * (unsigned long long)cols_done);
+            }
             __syncwarp();
         }
     }
