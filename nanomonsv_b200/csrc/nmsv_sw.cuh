@@ -658,6 +658,7 @@ sw_wavefront_kernel(const SwParams p)
         uint32_t sat = 0;          // bit h: half h came within 32 steps of the cap
         const uint32_t hi = task.hi;          // abandon the task when a score reaches hi (0: never)
         int cols_done = ncols;                // columns this tile went through (fewer when the task was abandoned)
+        int left_at = -1;                     // step at which an abandoned task was left (-1: ran to the end)
 
         {
             const int row0 = tile * 32 * R + lane * R;
@@ -891,7 +892,7 @@ sw_wavefront_kernel(const SwParams p)
                 __syncwarp();
                 // ---- abandoned task (some tile saw a score >= hi)? No bulk copy is in flight at this point.
                 if (hi) {
-                    if (__any_sync(kFull, ld_vol(&slot->abort) != 0u)) { cols_done = t0 < ncols ? t0 : ncols; break; }
+                    if (__any_sync(kFull, ld_vol(&slot->abort) != 0u)) { left_at = t0; cols_done = t0 < ncols ? t0 : ncols; break; }
                 }
                 // ---- TMA prefetch of the NEXT chunk of the read into the free ring slot (twice: the ring is mirrored);
                 //      it lands while this chunk is computed. Needs 16-byte aligned addresses and a whole chunk; the
@@ -986,8 +987,9 @@ sw_wavefront_kernel(const SwParams p)
                 }
             }
 
-            if (cols_done < ncols) {             // abandoned before the end
-                if (has_out) link_abort_fill(p, b_out, m_out, out_ring, q_out, cols_done - 31 > 0 ? cols_done - 31 : 0, ncols, lout);
+            if (left_at >= 0) {                  // abandoned: columns [0, left_at - 31) of the last row are out, the link is owed the rest
+                const int from = left_at - 31 > 0 ? (left_at - 31 < ncols ? left_at - 31 : ncols) : 0;
+                if (has_out) link_abort_fill(p, b_out, m_out, out_ring, q_out, from, ncols, lout);
             } else if (has_out && !out_ring) {   // the last group's stores, then the final count
                 __threadfence();
                 __syncwarp();
