@@ -71,6 +71,9 @@ class SynthConfig:
     sbnd: bool = False
     sbnd_contig_range: Tuple[int, int] = (200, 5000)
     sbnd_tail_range: Tuple[int, int] = (5000, 50000)
+    stratified: bool = False                   # SV kinds (and the short DEL/DUP share) in exact proportions per 40 candidates
+                                               # instead of independent draws: batches of a few hundred candidates then carry
+                                               # the same mix on every rank (bench.py: weak scaling compares like with like)
     seed: int = 20261019
 
 
@@ -212,6 +215,19 @@ def make_workload(cfg: SynthConfig, n_sv: Optional[int] = None, samples: Tuple[s
     probs = np.array([p for _, p in cfg.sv_mix], dtype=float)
     probs /= probs.sum()
 
+    pattern: List[Tuple[str, bool]] = []
+    if cfg.stratified and not cfg.sbnd:
+        # 40 slots in the proportions of sv_mix, the short ones spread over the DEL / DUP slots, in a fixed shuffled order
+        P = 40
+        counts = np.floor(probs * P + 1e-9).astype(int)
+        for j in np.argsort(-(probs * P - counts))[:P - int(counts.sum())]:
+            counts[j] += 1
+        slots = [k for k, c in zip(kinds, counts) for _ in range(int(c))]
+        dd = [j for j, k in enumerate(slots) if k in ("DEL", "DUP")]
+        n_short = int(round(cfg.short_fraction * len(dd)))
+        short_at = set(dd[int(round(q * len(dd) / max(n_short, 1)))] for q in range(n_short)) if dd else set()
+        order = np.random.default_rng(cfg.seed ^ 0x5eed).permutation(P)
+        pattern = [(slots[j], j in short_at) for j in order]
     svs: List[SynthSV] = []
     haps: List[Tuple[np.ndarray, int]] = []            # variant haplotype and junction position per SV
     bps: List[Tuple[Tuple[str, int], Optional[Tuple[str, int]]]] = []
@@ -234,17 +250,22 @@ def make_workload(cfg: SynthConfig, n_sv: Optional[int] = None, samples: Tuple[s
             bps.append(((c1, p1), None))
             continue
         kind = kinds[int(rng.choice(len(kinds), p=probs))]
+        is_short = None
+        if pattern:
+            kind, is_short = pattern[i % len(pattern)]
         ins = ""
         c2, d1, d2 = c1, "+", "-"
         if kind == "DEL":
-            span = int(rng.integers(60, 280)) if rng.random() < cfg.short_fraction else int(rng.integers(500, 50000))
+            u = rng.random()
+            span = int(rng.integers(60, 280)) if (u < cfg.short_fraction if is_short is None else is_short) else int(rng.integers(500, 50000))
             p2 = p1 + span
         elif kind == "INS":
             p2 = p1 + 1
             ilen = int(rng.integers(*cfg.ins_len_range))
             ins = codes_to_str(rng.integers(0, 4, size=ilen, dtype=np.uint8))
         elif kind == "DUP":
-            span = int(rng.integers(60, 280)) if rng.random() < cfg.short_fraction else int(rng.integers(500, 50000))
+            u = rng.random()
+            span = int(rng.integers(60, 280)) if (u < cfg.short_fraction if is_short is None else is_short) else int(rng.integers(500, 50000))
             p2 = p1 + span
             d1, d2 = "-", "+"
         elif kind == "INV":
