@@ -223,6 +223,8 @@ extern "C" int nmsv_create(nmsv_ctx** out, int device)
     // block-per-problem sw_jump kernel: three diagonals of the longest region it accepts (set once, not per call)
     CREATE_TRY(cudaFuncSetAttribute(sw_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(3ull * (kJumpMaxRegion + 2) * sizeof(int32_t))));
+    // warp-per-problem sw_jump kernel: 20 KB of strip rows per block, eight blocks per SM
+    CREATE_TRY(cudaFuncSetAttribute(sw_jump_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     {
         int g = 0;
         for (int c = 0; c < kNumClasses; ++c) g = std::max(g, ctx->prop.multiProcessorCount * std::max(1, ctx->blocks_per_sm[c]));
@@ -1749,7 +1751,13 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
             return set_err(ctx, NMSV_E_INVALID, "sw_jump problem %u: sequence index out of range", i);
         if (lens[a] > (uint32_t)kJumpMaxRegion || lens[b] > (uint32_t)kJumpMaxRegion)
             return set_err(ctx, NMSV_E_RANGE, "sw_jump problem %u: region longer than %d", i, kJumpMaxRegion);
-        if (std::max(lens[a], lens[b]) <= (uint32_t)kJumpWarpMaxRegion) {
+        // the warp kernel keeps its values times 32 in 32-bit lanes: it takes the problems whose scores stay below 2^23
+        // (every real one: a few thousand bases times a score of 1..3); anything else runs on the block kernel
+        const uint64_t unit = (uint64_t)std::max(std::max(std::abs((long long)params->match_score), std::abs((long long)params->mismatch_penalty)),
+                                                 std::abs((long long)params->gap_cost)) + 1;
+        const uint64_t bound = ((uint64_t)lens[c] + lens[a] + lens[b] + 4) * unit + 64ull * (uint64_t)std::abs((long long)params->jump_cost) +
+                               (uint64_t)std::abs((long long)params->minimum_score);
+        if (std::max(lens[a], lens[b]) <= (uint32_t)kJumpWarpMaxRegion && bound < (1ull << 23)) {
             JumpWarpProblem p;
             p.c_off = offsets[c]; p.r1_off = offsets[a]; p.r2_off = offsets[b];
             p.n = lens[c]; p.m1 = lens[a]; p.m2 = lens[b]; p.res_idx = i;
@@ -1789,10 +1797,10 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
         size_t last = first;
         while (last < wprobs.size()) {
             JumpWarpProblem& p = wprobs[last];
-            const uint64_t rows = (uint64_t)p.n + 1;
-            const uint64_t need = 64 * rows + 2 * rows + 2 + 2 * rows;      // two word matrices, rowbest, prefix (+pad), rowinfo
+            const uint64_t rows = (uint64_t)p.n + 1, wsteps = (uint64_t)p.n + 32;      // plane words are indexed by (step, lane)
+            const uint64_t need = 64 * wsteps + 2 * rows + 2 + 2 * rows;      // two word matrices, rowbest, prefix (+pad), rowinfo
             if (last > first && (words + need) * 8 > kMaxWorkBytes) break;
-            p.w1_off = words; p.w2_off = words + 32 * rows; p.row_off = words + 64 * rows;
+            p.w1_off = words; p.w2_off = words + 32 * wsteps; p.row_off = words + 64 * wsteps;
             words += need;
             ++last;
         }
@@ -1809,13 +1817,14 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
         wp.results = d_res.as<JumpResult>(); wp.ops = d_ops.as<uint8_t>();
         wp.match = params->match_score; wp.mismatch_penalty = params->mismatch_penalty; wp.gap_cost = params->gap_cost;
         wp.jump_cost = params->jump_cost; wp.minimum_score = params->minimum_score;
+        static const uint32_t jbps = getenv("NMSV_JUMP_BPS") ? (uint32_t)std::max(1, atoi(getenv("NMSV_JUMP_BPS"))) : 8u;   // tuning knob
         const uint32_t blocks = std::min<uint32_t>((cnt + kJumpWarpsPerBlock - 1) / kJumpWarpsPerBlock,
-                                                   (uint32_t)ctx->prop.multiProcessorCount * 8u);
+                                                   (uint32_t)ctx->prop.multiProcessorCount * jbps);
         static const bool jtrace = getenv("NMSV_TRACE") != nullptr;
         const auto jt0 = std::chrono::steady_clock::now();
         if (jtrace) cudaStreamSynchronize(s);
         const auto jt1 = std::chrono::steady_clock::now();
-        sw_jump_warp_kernel<<<blocks, kJumpWarpsPerBlock * 32, 0, s>>>(wp);
+        sw_jump_warp_kernel<<<blocks, kJumpWarpsPerBlock * 32, kJumpWarpsPerBlock * kJumpWarpSmem, s>>>(wp);
         CUDA_TRY(ctx, cudaGetLastError());
         CUDA_TRY(ctx, cudaStreamSynchronize(s));      // the host-side problem table of this chunk may be reused
         if (jtrace)

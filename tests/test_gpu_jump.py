@@ -89,3 +89,28 @@ def test_edge_shapes(engine):
     assert SW.sw_jump_batch([], engine=engine) == []
     with pytest.raises(ValueError):
         SW.sw_jump("", "A", "A", engine=engine)
+
+
+def test_every_strip_layout(engine):
+    """The warp kernel gives lanes 0..a-1 ceil(m/32) columns and the others one fewer, walks the strip in groups of four cells and
+    drops the phantom cells of the last group: region lengths around every boundary of that layout (multiples of 32 and of
+    128, one more, one less, shorter than a warp), both matrices independently, against the C oracle. Lengths above 1024 take
+    the block kernel; so does a scoring whose values would not fit the warp kernel's scaled 32-bit lanes."""
+    rnd = random.Random(77)
+    lens = [1, 2, 3, 5, 31, 32, 33, 34, 63, 64, 65, 95, 96, 97, 127, 128, 129, 130, 159, 160, 161, 255, 256, 257, 383, 384, 385,
+            511, 512, 513, 640, 641, 767, 768, 769, 895, 896, 897, 991, 992, 993, 1022, 1023, 1024, 1025, 1100]
+    probs = []
+    for k, m1 in enumerate(lens):
+        m2 = lens[(k * 7 + 3) % len(lens)]
+        probs.append(_junction_problem(rnd, 40, m1, m2, rnd.choice([0, 4]), 0.03))
+    for m in (1, 7, 32, 33, 100):           # contig shorter than a warp: the wavefront never fills
+        r1 = "".join(rnd.choice("ACGT") for _ in range(m))
+        r2 = "".join(rnd.choice("ACGT") for _ in range(m + 3))
+        probs.append((r1[:5] + r2[:6], r1, r2))
+    for prm in ((1, 3, 3, 2, 10), (2, 1, 4, 3, 6), (1, 1, 0, 1, 3)):
+        got = SW.sw_jump_batch(probs, *prm, engine=engine)
+        for (c, r1, r2), g in zip(probs, got):
+            assert g == O.sw_jump(c, r1, r2, *prm), (len(c), len(r1), len(r2), prm)
+    big = (300000, 3, 3, 2, 10)             # match score beyond the warp kernel's range: block kernel, same answers
+    few = probs[10:16]
+    assert SW.sw_jump_batch(few, *big, engine=engine) == [O.sw_jump(c, r1, r2, *big) for c, r1, r2 in few]
