@@ -278,7 +278,8 @@ typedef struct {
 } nmsv_jump_result;
 
 /* ops of problem p start at sum over q < p of (2*n_q + m1_q + m2_q + 4) bytes (n = contig length, m = region
- * lengths); ops_capacity must cover the sum over all problems. log_table[d] = ln(d) for d < log_table_len may be
+ * lengths); ops_capacity must cover the sum over all problems; only the first n_ops2 + n_ops1 bytes of a problem's
+ * segment are written, the rest of it is left as the caller passed it. log_table[d] = ln(d) for d < log_table_len may be
  * supplied by the caller (numpy's log in the Python layer, so that results are bit-identical to the reference);
  * distances beyond the table use the C library's log. */
 int nmsv_sw_jump_batch(nmsv_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, const uint64_t *offsets,

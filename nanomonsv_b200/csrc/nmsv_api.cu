@@ -87,6 +87,8 @@ struct nmsv_ctx {
     uint32_t ring_cols = 1024;
     int prune = 1;             // nmsv_set_option("prune"): skip alignments that cannot change any output
     int jump_bps = 0;          // resident blocks per SM of the sw_jump kernel (set once)
+    void* jump_stage = nullptr;      // pinned staging buffer of nmsv_sw_jump_batch (traceback operations on their way back)
+    size_t jump_stage_bytes = 0;
     mutable std::string error;
 };
 
@@ -223,8 +225,6 @@ extern "C" int nmsv_create(nmsv_ctx** out, int device)
     // block-per-problem sw_jump kernel: three diagonals of the longest region it accepts (set once, not per call)
     CREATE_TRY(cudaFuncSetAttribute(sw_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(3ull * (kJumpMaxRegion + 2) * sizeof(int32_t))));
-    // warp-per-problem sw_jump kernel: 20 KB of strip rows per block, eight blocks per SM
-    CREATE_TRY(cudaFuncSetAttribute(sw_jump_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     {
         int g = 0;
         for (int c = 0; c < kNumClasses; ++c) g = std::max(g, ctx->prop.multiProcessorCount * std::max(1, ctx->blocks_per_sm[c]));
@@ -260,6 +260,7 @@ extern "C" void nmsv_destroy(nmsv_ctx* ctx)
     if (ctx->snap) cudaFree(ctx->snap);
     if (ctx->rings) cudaFree(ctx->rings);
     if (ctx->ring_pos) cudaFree(ctx->ring_pos);
+    if (ctx->jump_stage) cudaFreeHost(ctx->jump_stage);
     delete ctx;
 }
 
@@ -1738,6 +1739,8 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
     if (rc) return rc;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
+    static const bool jtrace_all = getenv("NMSV_TRACE") != nullptr;
+    const auto ja0 = std::chrono::steady_clock::now();
 
     // Regions of up to kJumpWarpMaxRegion columns (every locate_bp call: +-20 bp around a read-supported breakpoint range, or
     // the first / last 500 bases of a contig) run one warp per problem; longer ones keep one block per problem.
@@ -1817,7 +1820,11 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
         wp.results = d_res.as<JumpResult>(); wp.ops = d_ops.as<uint8_t>();
         wp.match = params->match_score; wp.mismatch_penalty = params->mismatch_penalty; wp.gap_cost = params->gap_cost;
         wp.jump_cost = params->jump_cost; wp.minimum_score = params->minimum_score;
-        static const uint32_t jbps = getenv("NMSV_JUMP_BPS") ? (uint32_t)std::max(1, atoi(getenv("NMSV_JUMP_BPS"))) : 8u;   // tuning knob
+        // Two blocks = eight warps per SM, on purpose: the longest problems of a batch (a 2.6 kb contig against two 900-base
+        // regions is 5 200 steps of ~30 cells) set the length of the launch, and a warp that shares its scheduler with seven
+        // others walks them at an eighth of the issue rate. Measured on the 3000-problem set: 1 / 2 / 3 / 4 / 8 blocks per SM
+        // 9.6 / 6.2 / 6.3 / 8.1 / 9.4 ms (two warps per scheduler already issue ~0.7 instructions per clock).
+        static const uint32_t jbps = getenv("NMSV_JUMP_BPS") ? (uint32_t)std::max(1, atoi(getenv("NMSV_JUMP_BPS"))) : 2u;   // tuning knob
         const uint32_t blocks = std::min<uint32_t>((cnt + kJumpWarpsPerBlock - 1) / kJumpWarpsPerBlock,
                                                    (uint32_t)ctx->prop.multiProcessorCount * jbps);
         static const bool jtrace = getenv("NMSV_TRACE") != nullptr;
@@ -1873,8 +1880,32 @@ extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t 
         CUDA_TRY(ctx, cudaStreamSynchronize(s));      // the host-side problem table of this chunk may be reused
         first = last;
     }
+    const auto ja1 = std::chrono::steady_clock::now();
+    // The operations come back through a pinned staging buffer (a pageable destination moved 11 MB at 3.3 GB/s: 3.4 ms of a
+    // 12 ms call), and only the operations actually written -- about a quarter of the upper-bound layout, the path ends at
+    // the jump -- are copied on into the caller's array.
+    if (ops_total > ctx->jump_stage_bytes) {
+        if (ctx->jump_stage) cudaFreeHost(ctx->jump_stage);
+        ctx->jump_stage = nullptr; ctx->jump_stage_bytes = 0;
+        const size_t cap = std::max<size_t>(ops_total + ops_total / 4, (size_t)1 << 20);
+        CUDA_TRY(ctx, cudaHostAlloc(&ctx->jump_stage, cap, cudaHostAllocDefault));
+        ctx->jump_stage_bytes = cap;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(out, d_res.p, sizeof(JumpResult) * (size_t)n_problems, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ops, d_ops.p, ops_total, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->jump_stage, d_ops.p, ops_total, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    {
+        uint64_t off = 0;
+        const uint8_t* stage = static_cast<const uint8_t*>(ctx->jump_stage);
+        for (uint32_t i = 0; i < n_problems; ++i) {
+            const size_t cnt = (size_t)out[i].n_ops2 + out[i].n_ops1;
+            if (cnt) memcpy(ops + off, stage + off, cnt);
+            off += 2ull * lens[contig_idx[i]] + lens[region1_idx[i]] + lens[region2_idx[i]] + 4;
+        }
+    }
+    if (jtrace_all)
+        fprintf(stderr, "[nmsv] sw_jump: whole call up to the kernels' end %.2f ms, copy back of %.1f MB of results and operations %.2f ms\n",
+                std::chrono::duration<double, std::milli>(ja1 - ja0).count(), (ops_total + sizeof(JumpResult) * (double)n_problems) / 1e6,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ja1).count());
     return NMSV_OK;
 }

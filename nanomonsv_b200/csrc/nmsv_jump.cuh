@@ -398,7 +398,6 @@ __device__ __noinline__ JumpMatrixOut jump_matrix(const JumpWarpParams& p, const
             const int bj = max(bb, eq ? info.y : info.w);    // trunc(jump) joins before the chain
             best = __viaddmax_s32(hprev, mg32, bj);
             wj = push_sign(wj, max(bb, left) - (eq ? info.x : info.z));      // jump iff ceil(jump) > max(match, delete, insert)
-            lm = max(lm, best);
         } else {
             best = __viaddmax_s32(hprev, mg32, bb);
             run = __viaddmax_s32(best, kk, run);             // first maximum of the strip: cell index in the low bits
@@ -429,7 +428,7 @@ __device__ __noinline__ JumpMatrixOut jump_matrix(const JumpWarpParams& p, const
             int4 g = gl[0];
             uint32_t rcw = rl[0];
             int kq = 28;                                     // 31 - k of the group's first cell, minus 3
-#pragma unroll 1
+#pragma unroll 2
             for (int q = 0; q < ng - 1; ++q) {               // whole groups: every cell is this lane's own
                 const int4 gn = gl[(q + 1) * 32];            // next group, off the dependent chain
                 const uint32_t rcn = rl[(q + 1) * 32];
@@ -439,6 +438,7 @@ __device__ __noinline__ JumpMatrixOut jump_matrix(const JumpWarpParams& p, const
                 { const int keep = run; run = grun; o.x = cell(x, 0, g.x, 3); o.y = cell(x, 1, g.y, 2); o.z = cell(x, 2, g.z, 1); o.w = cell(x, 3, g.w, 0);
                   grun = run; run = keep; }
                 if (!kJump) run = __viaddmax_s32(grun, kq, run);
+                else lm = __vimax3_s32(__vimax3_s32(lm, o.x, o.y), o.z, o.w);      // matrix maximum, as G (two instructions per group)
                 gl[q * 32] = o;
                 kq -= 4;
                 g = gn; rcw = rcn;
@@ -449,13 +449,13 @@ __device__ __noinline__ JumpMatrixOut jump_matrix(const JumpWarpParams& p, const
                 const uint32_t x = rcw ^ c4;
                 int4 o;
                 o.x = cell(x, 0, g.x, kq + 3);
-                if (dcap >= 1) { left_cap = left; run_cap = run; lm_cap = lm; }
+                if (dcap >= 1) { left_cap = left; run_cap = run; lm_cap = max(lm_cap, left); }
                 o.y = cell(x, 1, g.y, kq + 2);
-                if (dcap >= 2) { left_cap = left; run_cap = run; lm_cap = lm; }
+                if (dcap >= 2) { left_cap = left; run_cap = run; lm_cap = max(lm_cap, left); }
                 o.z = cell(x, 2, g.z, kq + 1);
-                if (dcap >= 3) { left_cap = left; run_cap = run; lm_cap = lm; }
+                if (dcap >= 3) { left_cap = left; run_cap = run; lm_cap = max(lm_cap, left); }
                 o.w = cell(x, 3, g.w, kq);
-                if (dcap >= 4) { left_cap = left; run_cap = run; lm_cap = lm; }
+                if (dcap >= 4) { left_cap = left; run_cap = run; lm_cap = max(lm_cap, left); }
                 gl[(ng - 1) * 32] = o;
             }
             last_out = left_cap;
@@ -466,7 +466,7 @@ __device__ __noinline__ JumpMatrixOut jump_matrix(const JumpWarpParams& p, const
                 if (lane == 31) rowbest[i] = jpack(rbv >> kJumpScaleShift, (uint32_t)rbj);
                 words[(size_t)t * 32 + lane] = make_uint2(wdel & ~wins, wins);
             } else {
-                lmax = max(lmax, lm_cap);
+                lmax = max(lmax, lm_cap + g32);                      // lm is kept as G = 32 H - 32 g
                 const int hl = last_out + g32;                       // lane 31: H(i, m) x 32
                 if (hl > lc_v) { lc_v = hl; lc_i = i; }              // strict: the first row keeps a tie
                 words[(size_t)t * 32 + lane] = make_uint2(wj | (wdel & ~wins), wins | wj);
@@ -625,7 +625,7 @@ __device__ __forceinline__ void jump_warp_problem(const JumpWarpParams& p, const
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kJumpWarpsPerBlock * 32, 8) sw_jump_warp_kernel(const JumpWarpParams p)
+__global__ void __launch_bounds__(kJumpWarpsPerBlock * 32, 4) sw_jump_warp_kernel(const JumpWarpParams p)
 {
     extern __shared__ __align__(16) uint8_t jwsm[];
     uint8_t* const wsm = jwsm + (size_t)(threadIdx.x >> 5) * kJumpWarpSmem;
