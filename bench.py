@@ -746,6 +746,11 @@ def main():
             strong = _strong(torch, dist, dev, eng, rank, world, args)
             if rank == 0:
                 line["strong"] = strong
+    # ---- SURVEY 8(f) "next" row 2, driver-visible: sw_jump (breakpoint refinement) through nmsv_sw_jump_batch
+    if rank == 0 and world == 1 and not args.no_configs:
+        line["next_rows"] = {"sw_jump": sw_jump_entry(eng, check=0 if args.no_cpu_baseline else 40)}
+        log(f"[sw_jump] {line['next_rows']['sw_jump']['abi_gcells_per_s']:.0f} Gcells/s through the C ABI, "
+            f"parity {line['next_rows']['sw_jump']['parity_checked']} problems")
     if rank == 0:
         configs.sort(key=lambda c: c["baseline_config"])
         line["configs"] = configs
@@ -759,6 +764,34 @@ def main():
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sw_jump_entry(eng, n: int = 3000, check: int = 40) -> dict:
+    """The 3000 locate_bp-shaped problems of bench_jump.py (reference smith_waterman.py:5-127) through the C ABI with host
+    buffers; the first `check` problems are held to the C restatement of the reference's function (oracle/nmsv_jump_oracle.c,
+    itself pinned on vectors made by the reference)."""
+    import bench_jump
+    from nanomonsv_b200 import smith_waterman as SW
+    probs = bench_jump.problems(n)
+    cells = sum((len(c) + 1) * (len(a) + len(b) + 2) for c, a, b in probs)
+    SW.sw_jump_batch(probs, 1, 3, 3, 2, 10, engine=eng)          # grows the stream-ordered pool and the staging buffers once
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        got = SW.sw_jump_batch(probs, 1, 3, 3, 2, 10, engine=eng)
+        dt = time.perf_counter() - t0
+        best = SW.sw_jump_batch.last_abi_seconds if best is None else min(best, SW.sw_jump_batch.last_abi_seconds)
+    if check:
+        from oracle import oracle as O
+        for (c, a, b), g in zip(probs[:check], got[:check]):
+            if g != O.sw_jump(c, a, b, 1, 3, 3, 2, 10):
+                raise SystemExit("sw_jump: the CUDA path differs from the oracle")
+    return {"problems": n, "cells": cells, "abi_ms": best * 1e3, "abi_gcells_per_s": cells / best / 1e9,
+            "python_mirror_problems_per_s": n / dt, "found": sum(g is not None for g in got), "parity_checked": check,
+            "bound": "instruction issue of 8 resident warps per SM (13.6 / 18.4 instructions per H1 / H2 cell) and the length of "
+                     "the longest problem; path planes 2 bits per cell: HBM below 5 % of its peak",
+            "what": "two linear-gap DP matrices with a logarithmic jump + traceback per problem (contig x region1, contig x region2), "
+                    "regions 60-900 bases, contigs up to 2.6 kb; host strings in, result tuples and traceback operations out"}
 
 
 def _strong(torch, dist, dev, eng, rank, world, args):
