@@ -288,6 +288,17 @@ int nmsv_sw_jump_batch(nmsv_ctx *ctx, const uint8_t *bytes, uint64_t n_bytes, co
                        const double *log_table, uint32_t log_table_len, nmsv_jump_result *out, uint8_t *ops,
                        uint64_t ops_capacity);
 
+/* Host-side companion (no GPU work, no context): the two alignment rows of sw_jump's return value -- the contig row and the
+ * region row, each "<H1 part> <H2 part>" with '-' for gaps (nanomonsv/smith_waterman.py:61-125) -- written out from the
+ * traceback operations that nmsv_sw_jump_batch returned. The rows of problem p start at the same offset as its `ops`
+ * segment (row_offsets[p] = sum over q < p of 2*n_q + m1_q + m2_q + 4) in `contig_rows` / `region_rows` and are
+ * n_ops1 + 1 + n_ops2 bytes long; nothing is written for a problem with found == 0. Returns NMSV_E_INVALID if a
+ * traceback walks off its sequences (the operations do not belong to these sequences). */
+int nmsv_sw_jump_strings(const uint8_t *bytes, const uint64_t *offsets, const uint32_t *lens, const uint32_t *contig_idx,
+                         const uint32_t *region1_idx, const uint32_t *region2_idx, uint32_t n_problems,
+                         const nmsv_jump_result *results, const uint8_t *ops, const uint64_t *row_offsets,
+                         uint8_t *contig_rows, uint8_t *region_rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,7 +71,7 @@ EXPORTS = ["nmsv_abi_version", "nmsv_device_count", "nmsv_create", "nmsv_destroy
            "nmsv_device_info", "nmsv_encode_ascii", "nmsv_encode_pack", "nmsv_encode_pack_padded", "nmsv_seam_scan", "nmsv_ssw_batch", "nmsv_ssw_check_batch", "nmsv_validate_batch",
            "nmsv_plan_create", "nmsv_plan_run", "nmsv_plan_download", "nmsv_plan_stats", "nmsv_plan_download_alns",
            "nmsv_plan_destroy", "nmsv_plan_set_profiling", "nmsv_plan_kernel_times", "nmsv_plan_copy_counts_device",
-           "nmsv_measure_dpx_peak", "nmsv_sw_jump_batch"]
+           "nmsv_measure_dpx_peak", "nmsv_sw_jump_batch", "nmsv_sw_jump_strings"]
 
 _lib = None
 
@@ -162,5 +162,7 @@ def load() -> ctypes.CDLL:
     L.nmsv_sw_jump_batch.argtypes = [vp, vp, u64, vp, vp, u32, vp, vp, vp, u32, ctypes.POINTER(JumpParams), vp, u32, vp,
                                      vp, u64]
     L.nmsv_sw_jump_batch.restype = ctypes.c_int
+    L.nmsv_sw_jump_strings.argtypes = [vp, vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, vp]
+    L.nmsv_sw_jump_strings.restype = ctypes.c_int
     _lib = L
     return L

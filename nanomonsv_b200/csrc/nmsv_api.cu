@@ -1724,6 +1724,53 @@ extern "C" int nmsv_ssw_check_batch(nmsv_ctx* ctx, const uint8_t* codes, uint64_
 // ------------------------------------------------------------------------------------------------------------------
 // "next" row: sw_jump (reference smith_waterman.py:5-127)
 // ------------------------------------------------------------------------------------------------------------------
+// One traceback written out backwards (reference smith_waterman.py:71-125): operation 1 consumes a base of both sequences,
+// 2 a contig base against a gap, 3 a region base against a gap, 4 (the jump cell, H2 part only) shows both bases without moving.
+static bool jump_walk(const uint8_t* c, uint32_t nc, const uint8_t* r, uint32_t nr, int32_t i, int32_t j, const uint8_t* ops,
+                      uint32_t n, uint8_t* oc, uint8_t* og)
+{
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint8_t o = ops[k];
+        const bool uc = o == 1 || o == 2 || o == 4, ur = o == 1 || o == 3 || o == 4;
+        if ((uc && (i < 1 || (uint32_t)i > nc)) || (ur && (j < 1 || (uint32_t)j > nr)) || o < 1 || o > 4) return false;
+        oc[n - 1 - k] = uc ? c[i - 1] : (uint8_t)'-';
+        og[n - 1 - k] = ur ? r[j - 1] : (uint8_t)'-';
+        if (o == 1 || o == 2) --i;
+        if (o == 1 || o == 3) --j;
+    }
+    return true;
+}
+
+extern "C" int nmsv_sw_jump_strings(const uint8_t* bytes, const uint64_t* offsets, const uint32_t* lens,
+                                    const uint32_t* contig_idx, const uint32_t* region1_idx, const uint32_t* region2_idx,
+                                    uint32_t n_problems, const nmsv_jump_result* results, const uint8_t* ops,
+                                    const uint64_t* row_offsets, uint8_t* contig_rows, uint8_t* region_rows)
+{
+    if (n_problems == 0) return NMSV_OK;
+    if (!bytes || !offsets || !lens || !contig_idx || !region1_idx || !region2_idx || !results || !ops || !row_offsets ||
+        !contig_rows || !region_rows)
+        return NMSV_E_INVALID;
+    for (uint32_t p = 0; p < n_problems; ++p) {
+        const nmsv_jump_result& r = results[p];
+        if (!r.found) continue;
+        const uint32_t ci = contig_idx[p], ai = region1_idx[p], bi = region2_idx[p];
+        const uint64_t cap = 2ull * lens[ci] + lens[ai] + lens[bi] + 4ull;
+        if ((uint64_t)r.n_ops1 + r.n_ops2 + 1ull > cap) return NMSV_E_INVALID;
+        const uint8_t* o = ops + row_offsets[p];
+        uint8_t* oc = contig_rows + row_offsets[p];
+        uint8_t* og = region_rows + row_offsets[p];
+        // "<H1 part> <H2 part>": the operations hold the H2 part first (the traceback starts there)
+        if (!jump_walk(bytes + offsets[ci], lens[ci], bytes + offsets[ai], lens[ai], r.i1_end, r.j1_end, o + r.n_ops2, r.n_ops1, oc, og))
+            return NMSV_E_INVALID;
+        oc[r.n_ops1] = (uint8_t)' ';
+        og[r.n_ops1] = (uint8_t)' ';
+        if (!jump_walk(bytes + offsets[ci], lens[ci], bytes + offsets[bi], lens[bi], r.i2_end, r.j2_end, o, r.n_ops2,
+                       oc + r.n_ops1 + 1, og + r.n_ops1 + 1))
+            return NMSV_E_INVALID;
+    }
+    return NMSV_OK;
+}
+
 extern "C" int nmsv_sw_jump_batch(nmsv_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* offsets,
                                   const uint32_t* lens, uint32_t n_seqs, const uint32_t* contig_idx,
                                   const uint32_t* region1_idx, const uint32_t* region2_idx, uint32_t n_problems,

@@ -1,7 +1,8 @@
 """GPU-backed drop-in for nanomonsv/smith_waterman.py (reference v0.8.0): `sw_jump` with the reference's signature
 and return value (smith_waterman.py:5-127), called by locate_bp.get_refined_bp (locate_bp.py:37,67), plus a batched
-form. The DP and the traceback run in CUDA (csrc/nmsv_jump.cuh) behind nmsv_sw_jump_batch; only the two alignment
-strings of the return value are assembled here from the traceback operations."""
+form. The DP and the traceback run in CUDA (csrc/nmsv_jump.cuh) behind nmsv_sw_jump_batch; the two alignment
+strings of the return value are written out from the traceback operations by the library's host-side companion
+nmsv_sw_jump_strings."""
 from __future__ import annotations
 
 import ctypes
@@ -11,33 +12,6 @@ import numpy as np
 
 from . import _lib
 from .engine import Engine, default_engine
-
-
-_DASH = np.uint8(ord("-"))
-
-
-def _walk(seq_c: np.ndarray, seq_r: np.ndarray, i_end: int, j_end: int, ops: np.ndarray) -> Tuple[bytes, bytes]:
-    """Alignment rows of one traceback (reference smith_waterman.py:71-125), vectorised: operation k consumes a contig
-    base when its code is 1, 2 (or 4, the jump cell) and a region base when it is 1, 3 (or 4)."""
-    if len(ops) == 0:
-        return b"", b""
-    uses_c = (ops == 1) | (ops == 2) | (ops == 4)
-    uses_r = (ops == 1) | (ops == 3) | (ops == 4)
-    moves_c = (ops == 1) | (ops == 2)
-    moves_r = (ops == 1) | (ops == 3)
-    i = i_end - np.concatenate(([0], np.cumsum(moves_c[:-1])))
-    j = j_end - np.concatenate(([0], np.cumsum(moves_r[:-1])))
-    c = np.where(uses_c, seq_c[np.clip(i - 1, 0, len(seq_c) - 1)], _DASH)
-    g = np.where(uses_r, seq_r[np.clip(j - 1, 0, len(seq_r) - 1)], _DASH)
-    return c[::-1].tobytes(), g[::-1].tobytes()
-
-
-def _strings(contig: str, region1: str, region2: str, r, ops: np.ndarray) -> Tuple[str, str]:
-    cb = np.frombuffer(contig.encode("latin-1"), dtype=np.uint8)
-    n2, n1 = int(r["n_ops2"]), int(r["n_ops1"])
-    c2, g2 = _walk(cb, np.frombuffer(region2.encode("latin-1"), dtype=np.uint8), int(r["i2_end"]), int(r["j2_end"]), ops[:n2])
-    c1, g1 = _walk(cb, np.frombuffer(region1.encode("latin-1"), dtype=np.uint8), int(r["i1_end"]), int(r["j1_end"]), ops[n2:n2 + n1])
-    return (c1 + b" " + c2).decode("latin-1"), (g1 + b" " + g2).decode("latin-1")
 
 
 def sw_jump_batch(problems: Sequence[Tuple[str, str, str]], match_score: int = 1, mismatch_penalty: int = 2,
@@ -81,15 +55,28 @@ def sw_jump_batch(problems: Sequence[Tuple[str, str, str]], match_score: int = 1
                                          ctypes.byref(prm), logtab.ctypes.data, len(logtab), out.ctypes.data,
                                          ops.ctypes.data, ops.size))
     sw_jump_batch.last_abi_seconds = time.perf_counter() - t0      # the C-ABI call alone (H2D, kernels, D2H), for bench_jump.py
+    # the two alignment rows per problem (reference :61-125), written by the library at the offsets of the operations
+    rows = getattr(eng, "_jump_rows", None)
+    if rows is None or rows[0].size < ops.size:
+        rows = (np.zeros(ops.size, dtype=np.uint8), np.zeros(ops.size, dtype=np.uint8))
+        eng._jump_rows = rows
+    row_off = np.ascontiguousarray(ops_off[:-1].astype(np.uint64))
+    eng._check(eng._L.nmsv_sw_jump_strings(data.ctypes.data, offsets.ctypes.data, lens.ctypes.data, cidx.ctypes.data,
+                                           aidx.ctypes.data, bidx.ctypes.data, n, out.ctypes.data, ops.ctypes.data,
+                                           row_off.ctypes.data, rows[0].ctypes.data, rows[1].ctypes.data))
+    cols = {f: out[f].tolist() for f in out.dtype.names}
+    starts = row_off.tolist()
+    crow, rrow = rows[0].data, rows[1].data
     res: List[Optional[tuple]] = []
-    for k, (contig, r1, r2) in enumerate(problems):
-        r = out[k]
-        if not r["found"]:
+    for k in range(n):
+        if not cols["found"][k]:
             res.append(None)
             continue
-        cm, rm = _strings(contig, r1, r2, r, ops[int(ops_off[k]):int(ops_off[k + 1])])
-        res.append((int(r["score"]), (int(r["i1_start"]), int(r["i1_end"]), int(r["i2_start"]), int(r["i2_end"])),
-                    (int(r["j1_start"]), int(r["j1_end"])), (int(r["j2_start"]), int(r["j2_end"])), cm, rm))
+        a = starts[k]
+        b = a + cols["n_ops1"][k] + 1 + cols["n_ops2"][k]
+        res.append((cols["score"][k], (cols["i1_start"][k], cols["i1_end"][k], cols["i2_start"][k], cols["i2_end"][k]),
+                    (cols["j1_start"][k], cols["j1_end"][k]), (cols["j2_start"][k], cols["j2_end"][k]),
+                    str(crow[a:b], "latin-1"), str(rrow[a:b], "latin-1")))
     return res
 
 

@@ -346,3 +346,59 @@ def test_seam_scan_grouping_capacity_and_errors():
     rc, off = _scan_all(b"only\tfour\t1\t2\n", 1 << 40, 0, 0, 16, 16)
     assert rc == _lib.E_INVALID and off == 0
     assert _scan_all(b"", 1, 0, 0, 4, 4) == ([], 0)
+
+
+def test_sw_jump_strings_reproduce_the_reference_rows():
+    """nmsv_sw_jump_strings (host side of the sw_jump row, no GPU work): fed with the traceback operations of the C oracle it
+    must write the two alignment rows of the reference's own return values (tests/golden/sw_jump_vectors.json, produced by
+    nanomonsv/smith_waterman.py:5-127 itself)."""
+    import json
+    L = _lib.load()
+    OL = O.lib()
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sw_jump_vectors.json")))["vectors"]
+    seqs, results, ops_segments = [], [], []
+    for v in vec:
+        c, a, b = (np.frombuffer(v[k].encode("latin-1"), dtype=np.uint8) for k in ("contig", "region1", "region2"))
+        with np.errstate(divide="ignore"):
+            logtab = np.log(np.arange(len(c) + 1))
+        res = O.JumpResult()
+        ops = np.zeros(2 * len(c) + len(a) + len(b) + 4, dtype=np.uint8)
+        assert OL.ora_sw_jump(c.ctypes.data, len(c), a.ctypes.data, len(a), b.ctypes.data, len(b), *v["params"],
+                              logtab.ctypes.data, ctypes.byref(res), ops.ctypes.data) == 0
+        seqs += [c, a, b]
+        results.append(tuple(getattr(res, n) for n, _ in O.JumpResult._fields_))
+        ops_segments.append(ops)
+    lens = np.array([len(s) for s in seqs], dtype=np.uint32)
+    offsets = np.zeros(len(seqs), dtype=np.uint64)
+    np.cumsum(lens[:-1].astype(np.uint64), out=offsets[1:])
+    data = np.concatenate(seqs)
+    n = len(vec)
+    idx = np.arange(3 * n, dtype=np.uint32)
+    cidx, aidx, bidx = (np.ascontiguousarray(idx[k::3]) for k in range(3))
+    out = np.array(results, dtype=_lib.JUMP_RESULT_DTYPE)
+    ops = np.concatenate(ops_segments)
+    row_off = np.zeros(n, dtype=np.uint64)
+    np.cumsum(np.array([len(o) for o in ops_segments[:-1]], dtype=np.uint64), out=row_off[1:])
+    crow, rrow = np.zeros(ops.size, dtype=np.uint8), np.zeros(ops.size, dtype=np.uint8)
+    assert L.nmsv_sw_jump_strings(data.ctypes.data, offsets.ctypes.data, lens.ctypes.data, cidx.ctypes.data, aidx.ctypes.data,
+                                  bidx.ctypes.data, n, out.ctypes.data, ops.ctypes.data, row_off.ctypes.data,
+                                  crow.ctypes.data, rrow.ctypes.data) == 0
+    checked = 0
+    for k, v in enumerate(vec):
+        if v["expected"] is None:
+            assert not out[k]["found"]
+            continue
+        a = int(row_off[k]); b = a + int(out[k]["n_ops1"]) + 1 + int(out[k]["n_ops2"])
+        assert crow[a:b].tobytes().decode("latin-1") == v["expected"][4]
+        assert rrow[a:b].tobytes().decode("latin-1") == v["expected"][5]
+        checked += 1
+    assert checked > 90
+    # operations that do not belong to the sequences are refused, not read out of bounds
+    bad = ops.copy()
+    k = next(i for i, v in enumerate(vec) if v["expected"] is not None)
+    bad[int(row_off[k]):int(row_off[k]) + int(out[k]["n_ops2"])] = 2       # walks the contig far beyond its start
+    big = out.copy(); big[k]["n_ops2"] = 2 * lens[3 * k] + lens[3 * k + 2] + 2; big[k]["n_ops1"] = 1
+    bad[int(row_off[k]):int(row_off[k]) + int(big[k]["n_ops2"]) + 1] = 2
+    assert L.nmsv_sw_jump_strings(data.ctypes.data, offsets.ctypes.data, lens.ctypes.data, cidx.ctypes.data, aidx.ctypes.data,
+                                  bidx.ctypes.data, n, big.ctypes.data, bad.ctypes.data, row_off.ctypes.data,
+                                  crow.ctypes.data, rrow.ctypes.data) == _lib.E_INVALID
