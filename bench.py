@@ -450,17 +450,37 @@ def pair_sweep_entry(torch, dist, dev, eng, rank, world, total_pairs, cpu_gcups,
     t0 = time.perf_counter()
     outs = [eng.ssw_check_batch(pack, t, r) for t, r in chunks]
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    red = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dt_serial = time.perf_counter() - t0
+    # the same batches with two calls in flight (two contexts, two host threads; ctypes releases the GIL), the way a caller
+    # with a stream of batches drives the library: the upload of a batch and the end of its launch (the longest reads of a
+    # batch finish last) run under the kernels of the other one
+    from concurrent.futures import ThreadPoolExecutor
+    from nanomonsv_b200 import Engine
+    eng2 = Engine(dev.index)
+    engines = (eng, eng2)
+    eng2.ssw_check_batch(pack, chunks[0][0][:4096], chunks[0][1][:4096])     # warm-up of the second context
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        t0 = time.perf_counter()
+        outs2 = list(pool.map(lambda kc: engines[kc[0] & 1].ssw_check_batch(pack, kc[1][0], kc[1][1]), enumerate(chunks)))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    eng2.close()
+    if any((a != b).any() for a, b in zip(outs, outs2)):
+        raise SystemExit("pair sweep: the results of the calls in flight differ from the serial ones")
+    red = torch.tensor([dt, dt_serial], dtype=torch.float64, device=dev)
     tot = torch.tensor([cells_my, float(len(t_my))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot)
-    dt = float(red[0])
+    dt, dt_serial = float(red[0]), float(red[1])
     out = np.concatenate(outs)
     entry = {"baseline_config": 5, "workload": "pair_sweep: m=400, reads 1-50 kb uniform, half carry the template at 8% error",
              "pairs": int(tot[1]), "n_gpus": world, "s": dt, "gcups": float(tot[0]) / dt / 1e9, "pairs_per_s": float(tot[1]) / dt,
-             "hits": int((out["score"] > 480).sum()),
+             "hits": int((out["score"] > 480).sum()), "calls_in_flight": 2,
+             "serial": {"s": dt_serial, "gcups": float(tot[0]) / dt_serial / 1e9, "note": "one call at a time"},
              "note": "through nmsv_ssw_check_batch (both strands + begin pass) with host buffers: H2D of the pool per batch and "
                      "D2H of the tuples are inside the time; max over ranks"}
     if rank == 0:      # oracle on a sample of this rank's pairs
