@@ -343,15 +343,34 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU implementation of the path (parasail is not installable here -> the oracle port)
 # ----------------------------------------------------------------------------------------------------------------
+def arm_config(n_cand: int, n_reads: int, code_bytes: int, l2_bytes: int, world: int) -> dict:
+    """`config` of the JSON line, the same object in both arms: the workload and the batch one GPU takes per step (rank 0's
+    batch; the CPU arm times a bounded sample of that batch per step and says which in cpu_baseline.sample)."""
+    return {"workload": f"{WORKLOAD} (BASELINE.json configs[1]): canonical SV candidates, 30x tumor + 30x control "
+                        f"ONT-like reads ~10 kb, 8% error, m=2000 templates",
+            "sv_candidates_per_gpu_per_step": int(n_cand), "reads_per_gpu_per_step": int(n_reads),
+            "read_bases_per_gpu_mb": round(code_bytes / 1e6, 1),
+            "l2": f"inputs ({code_bytes / 1e6:.0f} MB of read bases per GPU) exceed the {l2_bytes / 1e6:.0f} MB L2",
+            "parallelism": f"sv-shards x{world}, equal planned cells per GPU, one NCCL all-reduce of the count tables at the end of the job" if world > 1 else "single GPU"}
+
+
 def reference_arm(args, rank: int):
     if rank != 0:
         return
-    cfg, pack, svs, reads = build_batch(min(args.svs_per_gpu, 16), 0, args)
+    # rank 0's batch of the other arm (same generator, same seed, same size): each step times a bounded sample of it
+    cfg, pack, svs, reads = build_batch(args.svs_per_gpu, 0, args)
     threads = os.cpu_count() or 1
+    l2_bytes = 132644864          # B200; read from the device when there is one
+    try:
+        import torch
+        if torch.cuda.is_available():
+            l2_bytes = int(torch.cuda.get_device_properties(0).L2_cache_size)
+    except Exception:
+        pass
     # calibrate on a small sample, then size one step to ~args.cpu_seconds
     job = OracleJob(pack, svs, reads, 2e10)
     dt, used, _ = job.run(threads)
-    job = OracleJob(pack, svs, reads, max(2e10, job.cells / dt * args.cpu_seconds))
+    job = OracleJob(pack, svs, reads, max(2e10, job.cells / dt * args.ref_step_seconds))
     for _ in range(args.warmup):
         job.run(threads)
     t0 = time.perf_counter()
@@ -364,10 +383,10 @@ def reference_arm(args, rank: int):
     line = {"impl": "reference", "metric": "GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int8->int16 striped SIMD (AVX2)", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: m=2000 templates, ~10 kb reads, 8% error; bounded sample per step",
-                       "engine": "oracle/nmsv_striped.c (parasail-equivalent port; parasail itself is not installable here)"},
+            "config": arm_config(len(svs) // 2, len(reads), pack.finalize()[0].size, l2_bytes, args.gpus),
             "sv_per_s": job.n_svs / 2 / dt,
-            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": "port", "sample": sample,
+                             "engine": "oracle/nmsv_striped.c (parasail-equivalent port; parasail itself is not installable here)"},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -524,6 +543,7 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--svs-per-gpu", type=int, default=int(os.environ.get("NMSV_BENCH_SVS", "384")))
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU work per step of the baseline sample")
+    ap.add_argument("--ref-step-seconds", type=float, default=2.0, help="--impl reference: CPU work per step (a bounded sample of the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU-oracle leg (cpu_baseline and parity_sampled)")
     ap.add_argument("--no-configs", action="store_true", help="headline workload only")
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs of the config-5 sweep (whole job, all ranks)")
@@ -701,12 +721,7 @@ def main():
             "metric": "GCUPS", "value": cells_ref / (ms_step * 1e-3) / 1e9, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "s16x2 (int16 DPX lanes)", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD} (BASELINE.json configs[1]): canonical SV candidates, 30x tumor + 30x control "
-                                   f"ONT-like reads ~10 kb, 8% error, m=2000 templates",
-                       "sv_candidates_per_gpu_per_step": n_cand, "reads_per_gpu_per_step": int(len(reads)),
-                       "read_bases_per_gpu_mb": round(codes.size / 1e6, 1),
-                       "l2": f"inputs ({codes.size / 1e6:.0f} MB of read bases per GPU) exceed the {info['l2_bytes'] / 1e6:.0f} MB L2",
-                       "parallelism": f"sv-shards x{world}, equal planned cells per GPU, one NCCL all-reduce of the count tables at the end of the job" if world > 1 else "single GPU"},
+            "config": arm_config(n_cand, len(reads), codes.size, info["l2_bytes"], world),
             "sv_per_s": cand_total / (ms_step * 1e-3),
             "gcups_executed": cells_exec / (ms_step * 1e-3) / 1e9,
             "cells_reference_per_step": cells_ref, "cells_executed_per_step": cells_exec, "cells_pruned_per_step": cells_pruned,
