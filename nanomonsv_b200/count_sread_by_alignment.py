@@ -19,13 +19,12 @@ contig twice; strand ties go to '-'.
 """
 from __future__ import annotations
 
-import math
 import os
 import random
 import subprocess
 from dataclasses import dataclass, field
 from concurrent.futures import ThreadPoolExecutor
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 

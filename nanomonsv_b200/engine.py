@@ -7,8 +7,7 @@ from __future__ import annotations
 import ctypes
 import os
 import weakref
-from dataclasses import dataclass
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 

@@ -8,7 +8,7 @@ runs them in a process pool and concatenates the text outputs (run.py:324-379, :
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
 import numpy as np
 

@@ -11,8 +11,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
-from .engine import Engine, EngineError, SeqPack, default_engine
-from . import _lib
+from .engine import Engine, SeqPack, default_engine
 
 
 @dataclass(frozen=True)

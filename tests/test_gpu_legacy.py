@@ -4,7 +4,6 @@ predicate that tests ref1 twice). The expectation is restated here from long_rea
 oracle as the aligner."""
 import dataclasses
 
-import numpy as np
 import pytest
 
 from nanomonsv_b200 import long_read_validate as LRV

@@ -1,13 +1,11 @@
 """GPU tests at the FULL sizes of the BASELINE configs (templates of 2 kb and 6 kb, reads up to 50 kb, 601-base
 single-breakend templates) where the CPU oracle would take too long for every pair: size-independent properties of
 the alignment, plus oracle spot checks on a few pairs per shape."""
-import random
 
 import numpy as np
 import pytest
 
-from nanomonsv_b200 import SeqPack, _lib, synth
-from nanomonsv_b200.my_seq import reverse_complement
+from nanomonsv_b200 import SeqPack, synth
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu

@@ -5,7 +5,6 @@ import dataclasses
 import json
 import os
 
-import numpy as np
 import pytest
 
 from nanomonsv_b200 import count_sread_by_alignment as C
