@@ -13,8 +13,9 @@ no data-path collective; for N > 1 the per-SV counts are merged with one NCCL al
 value  = reference-equivalent forward DP cells (sum 2*m*n over every alignment parasail would run) / device time,
          inputs resident in HBM, CUDA events on the launching stream, max over ranks.
 e2e    = the same cells / wall time of nmsv_validate_batch called with pinned HOST buffers (H2D, planning, kernels, D2H
-         inside the timed region), two calls in flight (two contexts, two host threads) so that the upload of one step
-         overlaps the kernels of the previous one; `e2e.serial` is the same with one call at a time.
+         inside the timed region), measured two ways every run: two calls in flight (two contexts, two host threads, so that
+         the upload of one step overlaps the kernels of the previous one: `e2e.pipelined`) and one call at a time
+         (`e2e.serial`); `e2e.value` is the faster of the two and `calls_in_flight` says which.
 The device does not compute every cell the reference computes: identical templates of one SV (var1 == var2 without an
 insertion) are aligned once, reads whose mapping-quality test already fails are only counted, and reference-allele
 alignments are run only for reads that pass the variant tests -- the outputs are identical (`parity_sampled`, tests/).
@@ -728,9 +729,13 @@ def main():
             "reads_pruned_per_gpu_per_step": st["reads_pruned"],
             "supporting_reads_per_step": supp_total,
             "clocks": clocks,
-            "e2e": {"value": cells_ref / e2e_s / 1e9, "unit": "GCUPS", "ms_per_step": e2e_s * 1e3,
-                    "sv_per_s": cand_total / e2e_s, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(st["d2h_bytes"]), "calls_in_flight": 2,
+            # both ways of driving the public call are measured every run (max over ranks each); `value` is the faster one:
+            # with 8 ranks on one host the 16 concurrent uploads of the pipelined form can cost more than they hide
+            "e2e": {"value": cells_ref / min(e2e_s, e2e_serial_s) / 1e9, "unit": "GCUPS", "ms_per_step": min(e2e_s, e2e_serial_s) * 1e3,
+                    "sv_per_s": cand_total / min(e2e_s, e2e_serial_s), "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(st["d2h_bytes"]), "calls_in_flight": 2 if e2e_s <= e2e_serial_s else 1,
+                    "pipelined": {"value": cells_ref / e2e_s / 1e9, "ms_per_step": e2e_s * 1e3,
+                                  "note": "two nmsv_validate_batch calls in flight (two contexts, two host threads)"},
                     "serial": {"value": cells_ref / e2e_serial_s / 1e9, "ms_per_step": e2e_serial_s * 1e3,
                                "note": "one nmsv_validate_batch call at a time"}},
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
