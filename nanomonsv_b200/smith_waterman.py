@@ -21,17 +21,13 @@ def sw_jump_batch(problems: Sequence[Tuple[str, str, str]], match_score: int = 1
     if not problems:
         return []
     eng = engine or default_engine()
-    chunks, lens = [], []
-    for trio in problems:
-        for sq in trio:
-            if not sq:
-                raise ValueError("sw_jump: empty sequence")
-            chunks.append(np.frombuffer(sq.encode("latin-1"), dtype=np.uint8))
-            lens.append(len(sq))
-    lens = np.asarray(lens, dtype=np.uint32)
+    enc = [sq.encode("latin-1") for trio in problems for sq in trio]
+    lens = np.fromiter(map(len, enc), dtype=np.uint32, count=len(enc))
+    if not lens.all():
+        raise ValueError("sw_jump: empty sequence")
     offsets = np.zeros(len(lens), dtype=np.uint64)
     np.cumsum(lens[:-1].astype(np.uint64), out=offsets[1:])
-    data = np.ascontiguousarray(np.concatenate(chunks))
+    data = np.frombuffer(b"".join(enc), dtype=np.uint8)
     n = len(problems)
     idx = np.arange(3 * n, dtype=np.uint32)
     cidx, aidx, bidx = (np.ascontiguousarray(idx[k::3]) for k in range(3))
