@@ -296,41 +296,44 @@ def stage_seam_e2e(eng, wl, order, n_cand, checked, supporting, n_records) -> di
         # A job of the size the reference runs (thousands of candidates per sample) spends its time in the steady state of the
         # pipeline; the two short calls above pay its fill and drain twice per 0.2 s. The same candidates REPS times over under
         # different SV ids (the last field of the key; the templates only depend on the others):
-        REPS = 4
-        for sample in ("tumor", "control"):
-            tails = [(wl.svs[i].key, [f"\t{rd.rid}\t{rd.mapq1}\t{rd.mapq2}\t{synth.codes_to_str(rd.codes)}\n"
-                                      for rd in wl.samples[sample][i]]) for i in order]
-            with open(seams[sample] + ".long", "w") as h:
-                for rep in range(REPS):
-                    for key, lines in tails:
-                        k = key + (f"r{rep}" if rep else "")
-                        h.write("".join(k + t for t in lines))
-            del tails
-
-        def run_long():
-            t0 = time.perf_counter()
+        REPS = max(1, min(4, 1300 // max(1, n_cand)))      # ~1 200 candidates per sample
+        long_job = None
+        if REPS > 1:
             for sample in ("tumor", "control"):
-                C.count_sread_from_seam(seams[sample] + ".long", seams[sample] + ".lcount", seams[sample] + ".linfo", wl.fasta, False, 0,
-                                        1.2, engine=eng, validate_sequence_length=L)
-            return time.perf_counter() - t0
-        dt_long = min(run_long(), run_long())
-        lc, ls, l_info = [], [], 0
-        for sample in ("tumor", "control"):
-            rows = [line.rstrip("\n").split("\t") for line in open(seams[sample] + ".lcount")]
-            lc += [[int(f[-2]) for f in rows[r * len(order):(r + 1) * len(order)]] for r in range(REPS)]
-            ls += [[int(f[-1]) for f in rows[r * len(order):(r + 1) * len(order)]] for r in range(REPS)]
-            l_info += sum(1 for _ in open(seams[sample] + ".linfo"))
-        half = len(order)
-        exp_c = [[int(x) for x in checked[:half]]] * REPS + [[int(x) for x in checked[half:]]] * REPS
-        exp_s = [[int(x) for x in supporting[:half]]] * REPS + [[int(x) for x in supporting[half:]]] * REPS
-        if lc != exp_c or ls != exp_s or l_info != REPS * n_records:
-            raise SystemExit("stage seam (long job): the files differ from the device-resident results")
+                tails = [(wl.svs[i].key, [f"\t{rd.rid}\t{rd.mapq1}\t{rd.mapq2}\t{synth.codes_to_str(rd.codes)}\n"
+                                          for rd in wl.samples[sample][i]]) for i in order]
+                with open(seams[sample] + ".long", "w") as h:
+                    for rep in range(REPS):
+                        for key, lines in tails:
+                            k = key + (f"r{rep}" if rep else "")
+                            h.write("".join(k + t for t in lines))
+                del tails
+
+            def run_long():
+                t0 = time.perf_counter()
+                for sample in ("tumor", "control"):
+                    C.count_sread_from_seam(seams[sample] + ".long", seams[sample] + ".lcount", seams[sample] + ".linfo", wl.fasta, False, 0,
+                                            1.2, engine=eng, validate_sequence_length=L)
+                return time.perf_counter() - t0
+            dt_long = min(run_long(), run_long())
+            lc, ls, l_info = [], [], 0
+            for sample in ("tumor", "control"):
+                rows = [line.rstrip("\n").split("\t") for line in open(seams[sample] + ".lcount")]
+                lc += [[int(f[-2]) for f in rows[r * len(order):(r + 1) * len(order)]] for r in range(REPS)]
+                ls += [[int(f[-1]) for f in rows[r * len(order):(r + 1) * len(order)]] for r in range(REPS)]
+                l_info += sum(1 for _ in open(seams[sample] + ".linfo"))
+            half = len(order)
+            exp_c = [[int(x) for x in checked[:half]]] * REPS + [[int(x) for x in checked[half:]]] * REPS
+            exp_s = [[int(x) for x in supporting[:half]]] * REPS + [[int(x) for x in supporting[half:]]] * REPS
+            if lc != exp_c or ls != exp_s or l_info != REPS * n_records:
+                raise SystemExit("stage seam (long job): the files differ from the device-resident results")
+            long_job = {"sv_per_s": REPS * n_cand / dt_long, "s": dt_long, "candidates_per_sample": REPS * n_cand,
+                        "seam_gb_per_s": REPS * size / dt_long / 1e9, "files_equal_device_resident_results": True,
+                        "what": f"the same two calls on seam files holding the candidates {REPS} times over (different SV ids): "
+                                "the fill and drain of the pipeline weigh less, as in a job of the reference's size"}
         return {"sv_per_s": n_cand / dt, "s": dt, "seam_bytes": size, "seam_gb_per_s": size / dt / 1e9,
                 "files_equal_device_resident_results": same,
-                "long_job": {"sv_per_s": REPS * n_cand / dt_long, "s": dt_long, "candidates_per_sample": REPS * n_cand,
-                             "seam_gb_per_s": REPS * size / dt_long / 1e9, "files_equal_device_resident_results": True,
-                             "what": f"the same two calls on seam files holding the candidates {REPS} times over (different SV ids): "
-                                     "the fill and drain of the pipeline weigh less, as in a job of the reference's size"},
+                "long_job": long_job,
                 "what": "count_sread_from_seam(tumor) + (control): seam TSV on disk (page cache) -> sread_count / sread_info files; "
                         "one Python process, one GPU; nmsv_seam_scan + nmsv_encode_pack on the host, GPU batches on a worker thread"}
     finally:
@@ -578,7 +581,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
-    ap.add_argument("--svs-per-gpu", type=int, default=int(os.environ.get("NMSV_BENCH_SVS", "384")))
+    ap.add_argument("--svs-per-gpu", type=int, default=int(os.environ.get("NMSV_BENCH_SVS", "1024")),
+                    help="candidates drawn per GPU and step (the batch is cut at this many times the planned-cell budget per candidate); a launch of "
+                         "~0.45 s: the end of a launch, when the longest reads run at low occupancy, weighs 1 % instead of 3 % at 384")
     ap.add_argument("--cpu-seconds", type=float, default=8.0, help="CPU work per step of the baseline sample")
     ap.add_argument("--ref-step-seconds", type=float, default=2.0, help="--impl reference: CPU work per step (a bounded sample of the batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip every CPU-oracle leg (cpu_baseline and parity_sampled)")
