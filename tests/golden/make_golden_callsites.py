@@ -1,10 +1,12 @@
-"""Regenerates tests/golden/callsites_reference.json by running the REFERENCE'S OWN code of two other parasail.ssw call sites
+"""Regenerates tests/golden/callsites_reference.json by running the REFERENCE'S OWN code of three other parasail.ssw call sites
  from /root/reference, unmodified, on small synthetic inputs:
 
   * nanomonsv/locate_bp_sbnd.py:43-66   `locate_bp_sbnd(consensus_file, output_file, reference_fasta, debug)` with its helper
     get_refined_bp_sbnd (:14-40): matrix 1/-2, reference window vs the whole consensus;
   * nanomonsv/generate_consensus.py:100-127   `Consensus_generator.generate_paf_file(query_fasta, target_fasta, output_file)`:
-    matrix 2/-2, whole reads (incl. reads longer than 16 383 bases) as the first sequence.
+    matrix 2/-2, whole reads (incl. reads longer than 16 383 bases) as the first sequence;
+  * nanomonsv/post_proc.py:84-134   `Sv_filterer.filter_sv_insertion_match` on the reference's own `Sv` objects, driven in the pair
+    order of `apply_filters` (:226-232): junction sequence vs insertion sequence, both strands, matrix 2/-2.
 
 `pysam` and `parasail` are absent in this image and are replaced by stand-ins registered in sys.modules before the import
 (the same arrangement as make_golden_stage.py): pysam.FastaFile over in-memory contigs, parasail.ssw with numbers from this
@@ -159,15 +161,59 @@ def paf_case(rng, tmp):
             "returned": n, "parasail_error": [list(x) for x in me.parasail_error]}
 
 
+def filter_case(rng):
+    """SV list around two insertions: translocation-like junctions that are the two ends of the first insertion (one of them
+    written from the other strand), a junction with an unrelated partner, one far away, a short-insert SV, an SV that arrives
+    already filtered, and a second insertion a few bases away (its pairs are met after the first insertion has filtered them).
+    The stage loop is the one of Sv_filterer.apply_filters (post_proc.py:226-232); every decision is the reference's own
+    filter_sv_insertion_match (:84-134) on the reference's own Sv objects."""
+    import itertools
+    CONTIGS.clear()
+    CONTIGS["chrA"] = rand_seq(rng, 8000)
+    b = rand_seq(rng, 8000)
+    CONTIGS["chrB"] = b[:5100] + b[5100:5200].lower() + b[5200:]
+    src = CONTIGS["chrB"].upper()[5000:5300]
+    ins1_seq = mutate(rng, src, 0.02)
+    svs = [  # chr1, pos1, dir1, chr2, pos2, dir2, inseq, id, initial filter
+        ("chrA", 3003, "+", "chrB", 5001, "-", "---"[:0], "t1", []),
+        ("chrA", 2990, "+", "chrB", 7000, "-", "", "t2", []),
+        ("chrA", 6000, "+", "chrB", 5001, "-", "", "t3", []),
+        ("chrA", 3000, "+", "chrA", 3001, "-", ins1_seq, "ins1", []),
+        ("chrB", 5300, "+", "chrA", 3001, "-", "", "t4", []),
+        ("chrA", 3001, "-", "chrB", 5300, "+", "", "t5", []),
+        ("chrA", 3010, "+", "chrA", 3011, "-", rand_seq(rng, 80), "ins2", []),
+        ("chrA", 3005, "+", "chrB", 5003, "-", "ACGTACGTAC", "t6", []),
+        ("chrA", 3002, "+", "chrB", 5001, "-", "", "t7", ["Too_low_VAF"]),
+        ("chrA", 2998, "+", "chrB", 5000, "-", rand_seq(rng, 40), "t8", []),
+    ]
+    mod = load("post_proc")
+    objs = []
+    for c1, p1, d1, c2, p2, d2, inseq, sid, flt in svs:
+        o = mod.Sv(c1, p1, d1, c2, p2, d2, inseq, sid, 30, 10, 30, 0)
+        o.filter = list(flt)
+        objs.append(o)
+    f = object.__new__(mod.Sv_filterer)          # without __init__ (it opens files through pysam)
+    f.reference_h, f.min_indel_size, f.bp_dist_margin, f.validate_seg_len = _FastaFile(None), 50, 30, 100
+    for a, c in itertools.combinations(objs, 2):
+        if len(a.filter) > 0 or len(c.filter) > 0:
+            continue
+        if len(a.inseq) < f.min_indel_size and len(c.inseq) >= f.min_indel_size:
+            f.filter_sv_insertion_match(a, c)
+        elif len(c.inseq) < f.min_indel_size and len(a.inseq) >= f.min_indel_size:
+            f.filter_sv_insertion_match(c, a)
+    f.hout = open(os.devnull, "w")                # __del__ closes these
+    return {"contigs": dict(CONTIGS), "svs": [list(x[:8]) + [x[8]] for x in svs], "filters_after": [o.filter for o in objs]}
+
+
 def main():
     rng = np.random.default_rng(20261020)
     with tempfile.TemporaryDirectory() as tmp:
         fix = {"generator": "tests/golden/make_golden_callsites.py", "reference": "nanomonsv v0.8.0 (/root/reference), modules "
                "locate_bp_sbnd and generate_consensus imported unmodified; pysam / parasail stand-ins (parasail numbers from the oracle)",
-               "sbnd": sbnd_case(rng, tmp), "paf": paf_case(rng, tmp)}
+               "sbnd": sbnd_case(rng, tmp), "paf": paf_case(rng, tmp), "filter": filter_case(rng)}
     json.dump(fix, open(os.path.join(HERE, "callsites_reference.json"), "w"), indent=0)
     print("sbnd lines", len(fix["sbnd"]["output"]), "of", len(fix["sbnd"]["consensus_lines"]), "; paf lines", len(fix["paf"]["paf"]),
-          "returned", fix["paf"]["returned"])
+          "returned", fix["paf"]["returned"], "; filters", fix["filter"]["filters_after"])
 
 
 if __name__ == "__main__":

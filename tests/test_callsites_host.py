@@ -65,3 +65,23 @@ def test_generate_paf_file_host_logic(oracle_backed, tmp_path):
         S.ssw_batch = real
     assert n == d["returned"] - 1 and errors == [("read1", "cons_1")]
     assert of.read_text().splitlines() == d["paf"][:1] + d["paf"][2:]
+
+
+class _Sv:
+    def __init__(self, c1, p1, d1, c2, p2, d2, inseq, sid, flt):
+        self.chr1, self.pos1, self.dir1, self.chr2, self.pos2, self.dir2, self.inseq, self.sv_id = c1, p1, d1, c2, p2, d2, inseq, sid
+        self.filter = list(flt)
+
+
+def test_insertion_match_filter_host_logic(oracle_backed):
+    """Sv_filterer.filter_sv_insertion_match in the pair order of apply_filters (post_proc.py:84-134, :226-232): the filters
+    the reference's own method left on its own Sv objects."""
+    from nanomonsv_b200 import sv_filter as F
+    d = FIX["filter"]
+    svs = [_Sv(*row) for row in d["svs"]]
+    n = F.apply_insertion_match_filter(svs, _Fasta(d["contigs"]))
+    assert [s.filter for s in svs] == d["filters_after"]
+    assert n > 0 and n % 2 == 0
+    assert any(f == ["Duplicate_with_insertion"] for f in d["filters_after"]) and any(f == [] for f in d["filters_after"])
+    # nothing to examine: no alignment call at all
+    assert F.apply_insertion_match_filter([_Sv("chrA", 10, "+", "chrA", 500, "-", "", "x", [])], _Fasta(d["contigs"])) == 0

@@ -50,3 +50,18 @@ def test_generate_paf_file_equals_the_reference_run(engine, tmp_path):
     assert of.read_text().splitlines() == d["paf"]
     assert n == d["returned"] and [list(e) for e in errors] == d["parasail_error"]
     assert any(int(l.split("\t")[1]) > 16383 for l in d["paf"])      # whole reads beyond the old length limit are aligned
+
+
+class _Sv:
+    def __init__(self, c1, p1, d1, c2, p2, d2, inseq, sid, flt):
+        self.chr1, self.pos1, self.dir1, self.chr2, self.pos2, self.dir2, self.inseq, self.sv_id = c1, p1, d1, c2, p2, d2, inseq, sid
+        self.filter = list(flt)
+
+
+def test_insertion_match_filter_equals_the_reference_run(engine):
+    """post_proc.py:84-134 in the pair order of :226-232, all examined pairs as one GPU batch."""
+    from nanomonsv_b200 import sv_filter as F
+    d = FIX["filter"]
+    svs = [_Sv(*row) for row in d["svs"]]
+    n = F.apply_insertion_match_filter(svs, _Fasta(d["contigs"]), engine=engine)
+    assert [s.filter for s in svs] == d["filters_after"] and n >= 10
