@@ -21,65 +21,64 @@ from .my_seq import reverse_complement
 logger = logging.getLogger(__name__)
 
 
-def _problem(contig, fasta_file_ins, chr1, start1, end1, dir1, chr2, start2, end2, dir2, mode, rd_margin=20, i_margin=500):
-    """((first, region1, region2) for sw_jump, context for _finish)"""
-    start1 = max(1, start1)
-    start2 = max(1, start2)
-    if mode != "i":
-        ref_len1 = fasta_file_ins.get_reference_length(chr1)
-        ref_len2 = fasta_file_ins.get_reference_length(chr2)
-        bstart1, bend1 = max(int(start1) - rd_margin, 1), int(end1) + rd_margin
-        bstart2, bend2 = max(int(start2) - rd_margin, 1), int(end2) + rd_margin
-        if ref_len1 < bend1:
-            bend1 = ref_len1
-        if ref_len2 < bend2:
-            bend2 = ref_len2
-        region1_seq = fasta_file_ins.fetch(chr1, bstart1 - 1, bend1).upper()
-        region2_seq = fasta_file_ins.fetch(chr2, bstart2 - 1, bend2).upper()
-        if dir1 == '-':
-            region1_seq = reverse_complement(region1_seq)
-        if dir2 == '+':
-            region2_seq = reverse_complement(region2_seq)
-        return (contig, region1_seq, region2_seq), (mode, contig, dir1, dir2, bstart1, bend1, bstart2, bend2)
-    contig_start = contig[:min(i_margin, len(contig))]
-    contig_end = contig[-min(i_margin, len(contig)):]
-    region_seq = fasta_file_ins.fetch(chr1, max(0, start1 - 100), end2 + 100).upper()
-    return (region_seq, contig_start, contig_end), (mode, contig, len(contig_end), max(0, start1 - 100))
+def _window(fasta, chrom, lo, hi, margin):
+    """1-based inclusive [lo - margin, hi + margin] clipped to the contig (:23-29): (first, last, upper-case bases)."""
+    first = max(int(lo) - margin, 1)
+    last = min(int(hi) + margin, fasta.get_reference_length(chrom))
+    return first, last, fasta.fetch(chrom, first - 1, last).upper()
+
+
+def _problem(contig, fasta, chr1, start1, end1, dir1, chr2, start2, end2, dir2, mode, rd_margin=20, i_margin=500):
+    """(the three sequences for sw_jump in the order the reference passes them, what _finish needs besides the result)"""
+    start1, start2 = max(1, start1), max(1, start2)                              # :15-16
+    if mode == "i":
+        # insertion: the reference window plays the contig role, the two ends of the contig are the regions (:61-67)
+        n_end = min(i_margin, len(contig))
+        origin = max(0, start1 - 100)
+        window = fasta.fetch(chr1, origin, end2 + 100).upper()
+        return (window, contig[:n_end], contig[-n_end:]), ("i", contig, n_end, origin)
+    first1, last1, reg1 = _window(fasta, chr1, start1, end1, rd_margin)
+    first2, last2, reg2 = _window(fasta, chr2, start2, end2, rd_margin)
+    # both regions are presented in the direction the contig runs through them (:34-35)
+    if dir1 == '-':
+        reg1 = reverse_complement(reg1)
+    if dir2 == '+':
+        reg2 = reverse_complement(reg2)
+    return (contig, reg1, reg2), (mode, contig, dir1, dir2, first1, last1, first2, last2)
 
 
 def _finish(sret, ctx, h_log):
+    """(bp_pos1, bp_pos2, inseq) from a sw_jump result (:41-58, :69-84), None when sw_jump found nothing; writes the three log
+    lines of the reference."""
     if sret is None:
         return None
-    if ctx[0] != "i":
-        _, contig, dir1, dir2, bstart1, bend1, bstart2, bend2 = ctx
-        score, contig_align, region1_align, region2_align, contig_seq, region_seq = sret
-        bp_pos1 = bstart1 + region1_align[1] - 1 if dir1 == '+' else bend1 - region1_align[1] + 1
-        bp_pos2 = bstart2 + region2_align[0] - 1 if dir2 == '-' else bend2 - region2_align[0] + 1
-        if contig_align[2] - contig_align[1] == 1:
-            inseq = '---'
-        elif contig_align[2] - contig_align[1] > 1:
-            inseq = contig[(contig_align[1]):(contig_align[2] - 1)]
-            if dir1 == '-':
-                inseq = reverse_complement(inseq)
-        else:
-            logger.warning("Alignment inconsistent!!")
-        if h_log is not None:
-            print(score, contig_align, region1_align, region2_align, file=h_log)
-            print(contig_seq, file=h_log)
-            print(region_seq, file=h_log)
-        return (bp_pos1, bp_pos2, inseq)      # unassigned after the warning above: fails like the reference (:58)
-    _, contig, len_contig_end, origin = ctx
-    score, region_align, contig_start_align, contig_end_align, region_seq, contig_seq = sret
-    bp_pos1 = origin + region_align[1]
-    bp_pos2 = origin + region_align[2]
-    inseq_start = contig_start_align[1]
-    inseq_end = len(contig) - (len_contig_end - contig_end_align[0] + 1)
-    inseq = contig[inseq_start:(inseq_end + 1)]
+    score, first_aln, r1_aln, r2_aln, row_a, row_b = sret
     if h_log is not None:
-        print(score, region_align, contig_start_align, contig_end_align, file=h_log)
-        print(region_seq, file=h_log)
-        print(contig_seq, file=h_log)
-    return (bp_pos1, bp_pos2, inseq)
+        print(score, first_aln, r1_aln, r2_aln, file=h_log)
+        print(row_a, file=h_log)
+        print(row_b, file=h_log)
+    if ctx[0] == "i":
+        _, contig, n_end, origin = ctx
+        # first_aln = (start, end of the first fragment, start, end of the second) on the reference window
+        ins_from = r1_aln[1]
+        ins_to = len(contig) - (n_end - r2_aln[0] + 1)
+        return origin + first_aln[1], origin + first_aln[2], contig[ins_from:ins_to + 1]
+    _, contig, dir1, dir2, first1, last1, first2, last2 = ctx
+    # the last aligned base of region1 and the first aligned base of region2, back in forward coordinates
+    pos1 = first1 + r1_aln[1] - 1 if dir1 == '+' else last1 - r1_aln[1] + 1
+    pos2 = first2 + r2_aln[0] - 1 if dir2 == '-' else last2 - r2_aln[0] + 1
+    between = first_aln[2] - first_aln[1]                   # contig bases between the two fragments, plus one
+    if between == 1:
+        inseq = '---'
+    elif between > 1:
+        inseq = contig[first_aln[1]:first_aln[2] - 1]
+        if dir1 == '-':
+            inseq = reverse_complement(inseq)
+    else:
+        # overlapping fragments: the reference only warns here and then fails at its return statement, inseq never assigned
+        logger.warning("Alignment inconsistent!!")
+        raise UnboundLocalError("cannot access local variable 'inseq' where it is not associated with a value")
+    return pos1, pos2, inseq
 
 
 def get_refined_bp(contig, fasta_file_ins, chr1, start1, end1, dir1, chr2, start2, end2, dir2, mode, h_log, sw_jump_params,
