@@ -59,13 +59,20 @@ def _ssw(s1, s2, gap_open, gap_extend, matrix):
     return O.ssw(s1, s2, gap_open, gap_extend, matrix.match, matrix.mismatch)
 
 
+REAL_PARASAIL = None      # set by build(real_parasail=...): tests/test_vs_parasail.py re-runs the reference with the real engine
+
+
 def load(module):
     pysam = types.ModuleType("pysam")
     pysam.FastaFile = _FastaFile
     pysam.AlignmentFile = object
-    parasail = types.ModuleType("parasail")
-    parasail.matrix_create, parasail.ssw = (lambda a, m, x: _Matrix(a, m, x)), _ssw
+    parasail = REAL_PARASAIL
+    if parasail is None:
+        parasail = types.ModuleType("parasail")
+        parasail.matrix_create, parasail.ssw = (lambda a, m, x: _Matrix(a, m, x)), _ssw
     sys.modules["pysam"], sys.modules["parasail"] = pysam, parasail
+    for name in [k for k in sys.modules if k == "nanomonsv" or k.startswith("nanomonsv.")]:
+        del sys.modules[name]        # a module imported earlier holds the parasail it was imported with
     pkg = types.ModuleType("nanomonsv")
     pkg.__path__ = ["/root/reference/nanomonsv"]
     sys.modules["nanomonsv"] = pkg
@@ -205,12 +212,19 @@ def filter_case(rng):
     return {"contigs": dict(CONTIGS), "svs": [list(x[:8]) + [x[8]] for x in svs], "filters_after": [o.filter for o in objs]}
 
 
-def main():
+def build(real_parasail=None) -> dict:
+    global REAL_PARASAIL
+    REAL_PARASAIL = real_parasail
     rng = np.random.default_rng(20261020)
     with tempfile.TemporaryDirectory() as tmp:
         fix = {"generator": "tests/golden/make_golden_callsites.py", "reference": "nanomonsv v0.8.0 (/root/reference), modules "
                "locate_bp_sbnd and generate_consensus imported unmodified; pysam / parasail stand-ins (parasail numbers from the oracle)",
                "sbnd": sbnd_case(rng, tmp), "paf": paf_case(rng, tmp), "filter": filter_case(rng)}
+    return fix
+
+
+def main():
+    fix = build()
     json.dump(fix, open(os.path.join(HERE, "callsites_reference.json"), "w"), indent=0)
     print("sbnd lines", len(fix["sbnd"]["output"]), "of", len(fix["sbnd"]["consensus_lines"]), "; paf lines", len(fix["paf"]["paf"]),
           "returned", fix["paf"]["returned"], "; filters", fix["filter"]["filters_after"])

@@ -85,3 +85,22 @@ def test_insertion_match_filter_host_logic(oracle_backed):
     assert any(f == ["Duplicate_with_insertion"] for f in d["filters_after"]) and any(f == [] for f in d["filters_after"])
     # nothing to examine: no alignment call at all
     assert F.apply_insertion_match_filter([_Sv("chrA", 10, "+", "chrA", 500, "-", "", "x", [])], _Fasta(d["contigs"])) == 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/nanomonsv"), reason="the reference checkout is not on this box")
+def test_the_fixture_is_what_its_generator_writes():
+    """tests/golden/make_golden_callsites.py re-run here (reference code from /root/reference, oracle-backed parasail stand-in)."""
+    import sys
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    saved = {k: sys.modules[k] for k in list(sys.modules) if k in ("pysam", "parasail") or k == "nanomonsv" or k.startswith("nanomonsv.")}
+    sys.path.insert(0, golden)
+    try:
+        import make_golden_callsites as M
+        got = M.build()
+        for part in ("sbnd", "paf", "filter"):
+            assert got[part] == FIX[part], part
+    finally:
+        sys.path.remove(golden)
+        for k in [k for k in sys.modules if k in ("pysam", "parasail") or k == "nanomonsv" or k.startswith("nanomonsv.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

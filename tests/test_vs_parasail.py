@@ -113,3 +113,22 @@ def test_stage_fixture_is_reproduced_with_the_real_parasail(tmp_path):
         for mod in ("pysam", "nanomonsv", "nanomonsv.count_sread_by_alignment", "nanomonsv.my_seq", "nanomonsv.pyssw"):
             sys.modules.pop(mod, None)
         sys.modules["parasail"] = parasail
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/nanomonsv"), reason="the reference checkout is not on this box")
+def test_callsite_fixtures_are_reproduced_with_the_real_parasail():
+    """locate_bp_sbnd, generate_paf_file and filter_sv_insertion_match of the reference, re-run with the real parasail on the
+    generator's inputs, must write what tests/golden/callsites_reference.json holds (made with the oracle standing in)."""
+    sys.path.insert(0, GOLDEN)
+    try:
+        import make_golden_callsites as M
+        fix = json.load(open(os.path.join(GOLDEN, "callsites_reference.json")))
+        got = M.build(real_parasail=parasail)
+        assert got["sbnd"]["output"] == fix["sbnd"]["output"] and got["sbnd"]["log"] == fix["sbnd"]["log"]
+        assert got["paf"]["paf"] == fix["paf"]["paf"] and got["paf"]["parasail_error"] == fix["paf"]["parasail_error"]
+        assert got["filter"]["filters_after"] == fix["filter"]["filters_after"]
+    finally:
+        sys.path.remove(GOLDEN)
+        for mod in [k for k in sys.modules if k == "pysam" or k == "nanomonsv" or k.startswith("nanomonsv.")]:
+            sys.modules.pop(mod, None)
+        sys.modules["parasail"] = parasail
